@@ -1,0 +1,202 @@
+/* stag_b200 -- C ABI of the B200-native stochastic neighbour aggregation.
+ *
+ * Drop-in boundary for the ONE hot path of yuanqing-wang/stag:
+ * the per-edge(-per-channel) multiplicative noise draw + message scaling + segmented
+ * reduction that the reference reaches through
+ *     StagLayer.forward            stag/layers.py:84-113
+ *       -> rsample_noise           stag/layers.py:115-129   (noise [E,K])
+ *       -> _in_norm                stag/layers.py:8-36
+ *       -> base_layer.forward(graph=, feat=, edge_weight=)   stag/layers.py:109-113
+ *            -> graph.update_all(fn.u_mul_e, fn.sum|fn.mean) stag/zoo/gcn.py:63,95
+ *                                                            stag/zoo/graph_sage.py:57,72,86
+ * and, in training, through autograd of the same (transposed aggregation + SDDMM).
+ * The reference has no FFI of its own (pure Python over DGL); these entry points are
+ * what a ctypes stub inside stag/zoo/*.py binds instead of graph.update_all -- see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no torch/CUDA types in signatures: device pointers are passed as raw
+ *    pointers, the stream as `void*` (a cudaStream_t; NULL = legacy default stream).
+ *  - every buffer is allocated and owned by the caller (PyTorch's caching allocator);
+ *    the library never allocates persistent device memory and never frees caller memory.
+ *  - every function returns 0 (STAG_OK) or a negative STAG_E* code and never throws;
+ *    stag_last_error() returns a thread-local message for the last failure.
+ *  - all work is enqueued on the given stream; only stag_csx_build synchronises (it
+ *    returns the hub counts to the host), and the *_host convenience entry points.
+ *  - features are fp32 row-major; structure is int32 on device (E, N < 2^31); the COO
+ *    input is int64 as produced by DGL (g.edges()).
+ */
+#ifndef STAG_B200_H
+#define STAG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define STAG_API __attribute__((visibility("default")))
+#else
+#define STAG_API
+#endif
+
+enum {
+  STAG_OK = 0,
+  STAG_EINVAL = -1,       /* bad argument (null pointer, shape mismatch, unsupported combination) */
+  STAG_ECUDA = -2,        /* a CUDA runtime call or kernel launch failed */
+  STAG_EWORKSPACE = -3,   /* workspace too small; see the *_workspace_bytes query */
+  STAG_EUNSUPPORTED = -4  /* valid request that this build does not implement */
+};
+
+/* distribution of the multiplicative edge noise (stag/layers.py:115-129) */
+enum {
+  STAG_NOISE_NONE = 0,      /* w == 1: plain copy_u/sum aggregation (edge_weight=None, stag/zoo/gcn.py:59) */
+  STAG_NOISE_EXTERNAL = 1,  /* w read from a caller tensor [S,E,K] in ORIGINAL edge order (parity seam) */
+  STAG_NOISE_NORMAL = 2,    /* w = loc + scale*eps            torch/distributions/normal.py:82-85   */
+  STAG_NOISE_UNIFORM = 3,   /* w = low + u*(high-low)         torch/distributions/uniform.py:85-88  */
+  STAG_NOISE_BERNOULLI = 4  /* w = (u < probs)                torch/distributions/bernoulli.py:116-119 */
+};
+
+/* shape class of the distribution parameters before `expand([E,K])` (stag/layers.py:117-119) */
+enum {
+  STAG_PARAM_SCALAR = 0,       /* "r1":  one value                       */
+  STAG_PARAM_CHANNEL = 1,      /* "rc":  [K]                             */
+  STAG_PARAM_EDGE = 2,         /* "re":  [E,1]  (AmortizedDistribution)  */
+  STAG_PARAM_EDGE_CHANNEL = 3  /* "rec": [E,K]  (AmortizedDistribution)  */
+};
+
+/* One compressed adjacency (CSC when built by destination, CSR when built by source),
+ * as filled in by stag_csx_build.  All pointers are device pointers. */
+typedef struct StagGraph {
+  int64_t num_rows;          /* N: rows of this structure (dst nodes for CSC, src nodes for CSR) */
+  int64_t num_cols;          /* number of nodes on the other side                                */
+  int64_t num_edges;         /* E                                                                */
+  const int32_t* indptr;     /* [N+1] row pointers                                               */
+  const int32_t* indices;    /* [E]   other endpoint of each stored edge                         */
+  const int32_t* eid;        /* [E]   original COO position of each stored edge                  */
+  /* hub schedule: rows with more than stag_hub_threshold() stored edges are processed as
+   * segments of stag_hub_segment() edges and combined in a fixed order (deterministic). */
+  int32_t num_hubs;
+  int32_t num_hub_segs;
+  const int32_t* hub_rows;     /* [num_hubs]   row ids, increasing                */
+  const int32_t* hub_seg_ptr;  /* [num_hubs+1] first global segment of each hub   */
+} StagGraph;
+
+/* Noise specification.  Parameter pointers are DEVICE pointers (they are nn.Parameters /
+ * buffers of stag.distributions.ParametrizedDistribution, stag/distributions.py:93-144, or
+ * the per-edge outputs of AmortizedDistribution, :221-242), already in natural units
+ * (scale, not log_scale). */
+typedef struct StagNoise {
+  int32_t kind;          /* STAG_NOISE_*                                                        */
+  int32_t K;             /* noise width: D (per edge per channel) or 1 (per edge)               */
+  int32_t param_shape;   /* STAG_PARAM_*                                                        */
+  int32_t relu;          /* stag/layers.py:98-99                                                */
+  int32_t in_norm;       /* stag/layers.py:102-105 (_in_norm); forward / CSC pass only          */
+  int32_t sample_base;   /* global index of local sample 0 (MC-sample sharding across GPUs)     */
+  const float* p0;       /* loc | low | probs                                                   */
+  const float* p1;       /* scale | high | NULL                                                 */
+  const float* external; /* EXTERNAL: [S,E,K], original edge order                              */
+  uint64_t seed;         /* Philox key                                                          */
+  uint64_t offset;       /* Philox call counter: one per (layer, forward call)                  */
+} StagNoise;
+
+STAG_API const char* stag_last_error(void);
+STAG_API int stag_abi_version(void);
+STAG_API int stag_hub_threshold(void);
+STAG_API int stag_hub_segment(void);
+
+/* ---- on-device CSC / CSR builder ------------------------------------------------------
+ * Replaces DGL's COO->CSC/CSR conversion behind graph.update_all (stag/zoo/gcn.py:95) and
+ * graph.in_degrees()/out_degrees() (stag/zoo/gcn.py:68,101; stag/layers.py:21).
+ * Stable LSD radix sort by destination (by_dst=1) or source (by_dst=0): bit-exact
+ * indptr / indices / eid against a stable sort of the COO list.
+ *   hub_rows     capacity  E / stag_hub_threshold() + 1
+ *   hub_seg_ptr  capacity  E / stag_hub_threshold() + 2
+ *   counts_host  [2] host ints: {num_hubs, num_hub_segs}  (the call synchronises `stream`)
+ */
+STAG_API size_t stag_csx_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+STAG_API int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes,
+                   int by_dst, int32_t* indptr, int32_t* indices, int32_t* eid,
+                   int32_t* hub_rows, int32_t* hub_seg_ptr, int32_t* counts_host,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused stochastic aggregation ------------------------------------------------------
+ * Forward (CSC graph), replaces rsample_noise + relu + _in_norm + update_all(u_mul_e, sum):
+ *
+ *   out[s,v,c] = dst_scale[v] * sum_{j in row v} w_s[eid_j, c] * (src_scale[u_j] * x[s,u_j,c])
+ *
+ * with u_j = indices[j], w drawn inside the kernel (never stored) or read from
+ * noise->external.  With in_norm the sum is multiplied by indeg(v) / sum_j w_s[eid_j,c]
+ * (1 when that sum is 0) and that factor is written to norm_scale_out [S,N,K] if non-NULL.
+ * x_sample_stride = 0 shares one X [N,D] across the S samples (first layer);
+ * ld* are row strides in floats.  reduce='mean' is expressed through dst_scale.
+ *
+ * The same entry point run on the CSR graph with (src_scale, dst_scale) swapped and
+ * x := dOut is the transposed aggregation, i.e. dX of the backward pass.
+ */
+STAG_API size_t stag_spmm_workspace_bytes(const StagGraph* g, int32_t D, int32_t S);
+STAG_API int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, int64_t x_sample_stride,
+                  int32_t D, int32_t S, const StagNoise* noise,
+                  const float* src_scale, const float* dst_scale,
+                  float* out, int64_t ldo, int64_t out_sample_stride,
+                  float* norm_scale_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward with noise-parameter gradients (CSR graph; vi=True, stag/layers.py:123-124).
+ * One pass over the out-edges of every source node u regenerates w from (seed, offset) and emits
+ *   dx[s,u,c]     = src_scale[u] * sum_j w_s[eid_j,c] * g[s,v_j,c],   g = dst_scale[v]*dout[s,v,c]
+ *   dw[s,e,c]     = (src_scale[u]*x[s,u,c]) * g[s,v,c]                (SDDMM, never stored unless
+ *                                                                     EXTERNAL and dw_external != NULL)
+ *   NORMAL : dparam0 = sum dw (d loc), dparam1 = sum dw*eps (d scale)
+ *   UNIFORM: dparam0 = sum dw*(1-u) (d low), dparam1 = sum dw*u (d high)
+ * reduced to the parameter shape: SCALAR -> [1], CHANNEL -> [K], EDGE -> [E], EDGE_CHANNEL -> [E,K]
+ * (EDGE shapes require S == 1 and ACCUMULATE into dparam*, i.e. the caller zeroes them once).
+ * SCALAR / CHANNEL results OVERWRITE dparam* and are summed over the S samples.
+ * dx may be NULL (first layer: features need no gradient).  Not valid with in_norm.
+ */
+STAG_API int stag_spmm_bwd(const StagGraph* csr, const float* x, int64_t ldx, int64_t x_sample_stride,
+                  const float* dout, int64_t ldg, int64_t dout_sample_stride,
+                  int32_t D, int32_t S, const StagNoise* noise,
+                  const float* src_scale, const float* dst_scale,
+                  float* dx, int64_t lddx, int64_t dx_sample_stride,
+                  float* dparam0, float* dparam1, float* dw_external,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* Materialise the noise tensor w [S,E,K] (original edge order) from the same Philox stream
+ * the fused kernels use: compatibility path for base layers that are not fused
+ * (StagLayer._edge_weight_sample, stag/layers.py:107; KL fallback :141-143) and for RNG tests.
+ * eps_out (optional) receives the raw variate (standard normal / uniform) before loc/scale. */
+STAG_API int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_t S,
+                    float* w_out, float* eps_out, void* stream);
+
+/* Segmented readout over batch_num_nodes (SumNodes / MeanNodes, stag/layers.py:156-178):
+ * out[b,c] = sum (or mean) of feat rows in [node_ptr[b], node_ptr[b+1]). */
+STAG_API int stag_segment_reduce(const float* feat, int64_t ldf, const int32_t* node_ptr, int32_t num_graphs,
+                        int32_t D, int mean, float* out, int64_t ldo, void* stream);
+
+/* Dense feature transform agg @ W (stag/zoo/gcn.py:97-98) on tcgen05 tensor cores with TMEM
+ * accumulators; fp32 in / fp32 out computed as 3xTF32 (fp32-level accuracy), fused epilogue
+ *   out[m,n] = act( row_scale[m] * sum_k a[m,k]*w[k,n] + bias[n] ),  act: 0 none, 1 relu.
+ * wt is W transposed, [Nout, K] row-major (K-major). */
+STAG_API size_t stag_gemm_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
+STAG_API int stag_gemm_tcgen05(const float* a, int64_t lda, const float* wt, int64_t ldw,
+                      int64_t M, int32_t Nout, int32_t K,
+                      const float* row_scale, const float* bias, int act,
+                      float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
+
+/* Host-buffer convenience entry point (what bench.py's e2e leg and a non-torch caller use):
+ * COO graph, features and upstream gradient in HOST memory; builds CSC+CSR on the device,
+ * runs forward + backward for S samples with generated noise and copies out / dx back.
+ * Synchronous.  device = CUDA ordinal. */
+STAG_API int stag_aggregate_host(int device, const int64_t* src, const int64_t* dst, int64_t num_edges,
+                        int64_t num_nodes, const float* x, const float* dout, int32_t D, int32_t S,
+                        const StagNoise* noise_host_params, int gcn_norm_both,
+                        float* out, float* dx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAG_B200_H */

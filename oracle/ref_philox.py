@@ -1,0 +1,120 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the library's counter-based
+noise generator (stag_b200/csrc/noise.cuh), used by the GPU tests to check the
+fused RNG path bit-for-bit on the integer stream and to ~1e-5 on the transformed
+variates.  This part has no counterpart in the reference (which calls torch's
+global Philox generator through torch.distributions: stag/layers.py:117-127,
+torch/distributions/normal.py:82-85, uniform.py:85-88, bernoulli.py:116-119);
+bitwise parity with torch's stream is not a goal (SURVEY.md 8(c) "RNG") -- the law
+is what must agree, and tests/test_gpu_rng.py checks the law statistically.
+
+Generator: Philox4x32-10 (Salmon et al., SC'11; Random123 constants), pinned here
+against the Random123 known-answer vectors (tests/test_oracle_cpu.py).
+
+Counter / key layout (one 128-bit block = the 4 channels 4q..4q+3 of one edge):
+    ctr = (eid, q, sample, offset_lo)      key = (seed_lo, seed_hi ^ offset_hi)
+Variates from the four output words r0..r3:
+    m(r)   = float32 with bits 0x3f800000 | (r >> 9)           in [1, 2)
+    uniform:   u_i = m(r_i) - 1                                in [0, 1)
+    normal :   (z0, z1) from (r0, r1), (z2, z3) from (r2, r3) by Box-Muller,
+               rad = sqrt(-2 ln(2 - m(r_a))),  ang = 2*pi*m(r_b),
+               z_even = rad * cos(ang),  z_odd = rad * sin(ang)
+    bernoulli: 1 if u_i < p else 0
+A per-edge noise (K == 1) uses q = 0 and the first variate only.
+"""
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = np.uint32(0x9E3779B9)
+W1 = np.uint32(0xBB67AE85)
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10.  All arguments are broadcastable uint32 arrays."""
+    c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3)]
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0 = np.uint32(k0)
+    k1 = np.uint32(k1)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = M0 * c0.astype(np.uint64)
+            p1 = M1 * c2.astype(np.uint64)
+            hi0 = (p0 >> np.uint64(32)).astype(np.uint32)
+            lo0 = (p0 & MASK).astype(np.uint32)
+            hi1 = (p1 >> np.uint64(32)).astype(np.uint32)
+            lo1 = (p1 & MASK).astype(np.uint32)
+            c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+            k0 = np.uint32((int(k0) + int(W0)) & 0xFFFFFFFF)
+            k1 = np.uint32((int(k1) + int(W1)) & 0xFFFFFFFF)
+    return c0, c1, c2, c3
+
+
+def raw_block(eid, q, sample, seed, offset):
+    """The four 32-bit words for (edge, channel-quad, sample) under (seed, offset)."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    offset = int(offset) & 0xFFFFFFFFFFFFFFFF
+    k0 = seed & 0xFFFFFFFF
+    k1 = (seed >> 32) ^ (offset >> 32)
+    return philox4x32_10(eid, q, sample, np.uint32(offset & 0xFFFFFFFF), k0, k1)
+
+
+def mant(r):
+    return ((np.asarray(r, np.uint32) >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32)
+
+
+def raw_words(num_edges, K, sample, seed, offset):
+    """uint32 [E, K] -- word used for channel c of edge e (ORIGINAL edge order)."""
+    nq = (K + 3) // 4
+    eid = np.arange(num_edges, dtype=np.uint32)[:, None]
+    q = np.arange(nq, dtype=np.uint32)[None, :]
+    r = raw_block(eid, q, np.uint32(sample), seed, offset)
+    return np.stack(r, axis=-1).reshape(num_edges, nq * 4)[:, :K]
+
+
+def uniform(num_edges, K, sample, seed, offset):
+    return mant(raw_words(num_edges, K, sample, seed, offset)) - np.float32(1.0)
+
+
+def std_normal(num_edges, K, sample, seed, offset):
+    nq = (K + 3) // 4
+    eid = np.arange(num_edges, dtype=np.uint32)[:, None]
+    q = np.arange(nq, dtype=np.uint32)[None, :]
+    r0, r1, r2, r3 = raw_block(eid, q, np.uint32(sample), seed, offset)
+
+    def bm(ra, rb):
+        u = (np.float32(2.0) - mant(ra)).astype(np.float64)
+        rad = np.sqrt(-2.0 * np.log(u))
+        ang = 2.0 * np.pi * mant(rb).astype(np.float64)
+        return rad * np.cos(ang), rad * np.sin(ang)
+
+    z0, z1 = bm(r0, r1)
+    z2, z3 = bm(r2, r3)
+    z = np.stack([z0, z1, z2, z3], axis=-1).reshape(num_edges, nq * 4)[:, :K]
+    return z.astype(np.float32)
+
+
+def noise(kind, num_edges, K, sample, seed, offset, p0=None, p1=None, relu=False):
+    """w [E,K] float32 for a distribution kind in {'normal','uniform','bernoulli'};
+    p0/p1 broadcastable to [E,K] (loc/scale, low/high, probs)."""
+    if kind == "normal":
+        w = np.float32(p0) + std_normal(num_edges, K, sample, seed, offset) * np.float32(p1)
+    elif kind == "uniform":
+        w = np.float32(p0) + uniform(num_edges, K, sample, seed, offset) * (np.float32(p1) - np.float32(p0))
+    elif kind == "bernoulli":
+        w = (uniform(num_edges, K, sample, seed, offset) < np.float32(p0)).astype(np.float32)
+    else:
+        raise KeyError(kind)
+    w = np.asarray(w, dtype=np.float32)
+    return np.maximum(w, 0) if relu else w
+
+
+# Random123 known-answer vectors for philox4x32-10 (kat_vectors): (ctr, key, expected)
+KAT = [
+    ((0x00000000, 0x00000000, 0x00000000, 0x00000000), (0x00000000, 0x00000000),
+     (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff),
+     (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]

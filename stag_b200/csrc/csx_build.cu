@@ -1,0 +1,281 @@
+// On-device CSC / CSR builder: stable LSD radix sort of the COO edge list by
+// destination (CSC) or source (CSR), row pointers from the sorted keys, and the
+// hub-row schedule used by the aggregation kernels.
+//
+// Replaces DGL's COO->CSC/CSR conversion that the reference triggers through
+// graph.update_all (stag/zoo/gcn.py:95, stag/layers.py:12-15) and
+// graph.in_degrees()/out_degrees() (stag/zoo/gcn.py:68,101; stag/layers.py:21).
+// Bit-exact target: oracle/ref_index.py (stable argsort).
+#include "common.cuh"
+
+namespace stag {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;  // 4096 keys per CTA
+constexpr int RS_RADIX = 256;
+
+__global__ void k_init_keys(const int64_t* __restrict__ key64, int64_t E, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E) {
+    keys[i] = (uint32_t)key64[i];
+    vals[i] = (uint32_t)i;
+  }
+}
+
+// per-CTA digit histogram, stored digit-major: hist[d * nblocks + b]
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t* __restrict__ keys, int64_t E,
+                                                           int shift, uint32_t* __restrict__ hist, int nblocks) {
+  __shared__ uint32_t h[RS_RADIX];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    int64_t i = base + r * RS_THREADS + threadIdx.x;
+    if (i < E) atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// single-CTA exclusive scan, in place, n arbitrary.  Also returns the total in *total if non-null.
+__global__ void __launch_bounds__(1024) k_exclusive_scan(uint32_t* __restrict__ data, int64_t n,
+                                                        uint32_t* __restrict__ total) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + tid;
+    const uint32_t v = i < n ? data[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t s = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+      }
+      warp_sums[lane] = s;  // inclusive
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t warp_off = wid == 0 ? 0u : warp_sums[wid - 1];
+    if (i < n) data[i] = carry + warp_off + x - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_off + x;
+    __syncthreads();
+  }
+  if (tid == 0 && total) *total = carry_s;
+}
+
+// stable scatter of one CTA tile: ranks are assigned in (round, warp, lane) order, which is
+// the key order inside the tile.
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, int64_t E, int shift, const uint32_t* __restrict__ hist_scanned,
+    int nblocks) {
+  __shared__ uint32_t running[RS_RADIX];
+  __shared__ uint32_t warp_cnt[RS_WARPS][RS_RADIX];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  running[tid] = hist_scanned[(size_t)tid * nblocks + blockIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) warp_cnt[w][tid] = 0;
+    __syncthreads();
+    const int64_t i = base + r * RS_THREADS + tid;
+    const bool valid = i < E;
+    uint32_t key = 0, val = 0, digit = 0xffffffffu;
+    if (valid) {
+      key = keys_in[i];
+      val = vals_in[i];
+      digit = (key >> shift) & 0xff;
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) warp_cnt[wid][digit] = __popc(peers);
+    __syncthreads();
+    {
+      uint32_t run = running[tid];
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; ++w) {
+        const uint32_t c = warp_cnt[w][tid];
+        warp_cnt[w][tid] = run;
+        run += c;
+      }
+      running[tid] = run;
+    }
+    __syncthreads();
+    if (valid) {
+      const uint32_t pos = warp_cnt[wid][digit] + rank;
+      keys_out[pos] = key;
+      vals_out[pos] = val;
+    }
+    __syncthreads();
+  }
+}
+
+// indptr from sorted keys: indptr[v] = first position whose key >= v
+__global__ void k_indptr_from_sorted(const uint32_t* __restrict__ keys, int64_t E, int64_t N,
+                                     int32_t* __restrict__ indptr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > E) return;
+  const int64_t prev = i == 0 ? -1 : (int64_t)keys[i - 1];
+  const int64_t cur = i == E ? N : (int64_t)keys[i];
+  for (int64_t v = prev + 1; v <= cur; ++v) indptr[v] = (int32_t)i;
+}
+
+__global__ void k_gather_other(const uint32_t* __restrict__ eid_sorted, const int64_t* __restrict__ other64,
+                               int64_t E, int32_t* __restrict__ indices, int32_t* __restrict__ eid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E) {
+    const uint32_t e = eid_sorted[i];
+    eid[i] = (int32_t)e;
+    indices[i] = (int32_t)other64[e];
+  }
+}
+
+// hub schedule ---------------------------------------------------------------------------
+__global__ void k_hub_flags(const int32_t* __restrict__ indptr, int64_t N, uint32_t* __restrict__ is_hub,
+                            uint32_t* __restrict__ nseg) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N) {
+    const int deg = indptr[v + 1] - indptr[v];
+    const bool hub = deg > kHubThreshold;
+    is_hub[v] = hub ? 1u : 0u;
+    nseg[v] = hub ? (uint32_t)((deg + kHubSegment - 1) / kHubSegment) : 0u;
+  }
+}
+
+__global__ void k_hub_scatter(const int32_t* __restrict__ indptr, int64_t N, const uint32_t* __restrict__ hub_idx,
+                              const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ totals,
+                              int32_t* __restrict__ hub_rows, int32_t* __restrict__ hub_seg_ptr) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N) {
+    const int deg = indptr[v + 1] - indptr[v];
+    if (deg > kHubThreshold) {
+      hub_rows[hub_idx[v]] = (int32_t)v;
+      hub_seg_ptr[hub_idx[v]] = (int32_t)seg_off[v];
+    }
+  }
+  if (v == 0) hub_seg_ptr[totals[0]] = (int32_t)totals[1];
+}
+
+struct CsxWorkspace {
+  uint32_t *keys_a, *vals_a, *keys_b, *vals_b, *hist, *flags_a, *flags_b, *totals;
+  int nblocks;
+};
+
+static size_t carve(int64_t E, int64_t N, char* base, CsxWorkspace* w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 256);
+    return (uint32_t*)p;
+  };
+  const int nblocks = (int)((E + RS_TILE - 1) / RS_TILE);
+  const size_t e = (size_t)(E > 0 ? E : 1);
+  CsxWorkspace tmp;
+  tmp.nblocks = nblocks;
+  tmp.keys_a = take(e * 4);
+  tmp.vals_a = take(e * 4);
+  tmp.keys_b = take(e * 4);
+  tmp.vals_b = take(e * 4);
+  tmp.hist = take((size_t)RS_RADIX * (nblocks > 0 ? nblocks : 1) * 4);
+  tmp.flags_a = take((size_t)(N + 1) * 4);
+  tmp.flags_b = take((size_t)(N + 1) * 4);
+  tmp.totals = take(256);
+  if (w) *w = tmp;
+  return off;
+}
+
+}  // namespace stag
+
+using namespace stag;
+
+extern "C" size_t stag_csx_workspace_bytes(int64_t num_edges, int64_t num_nodes) {
+  return carve(num_edges, num_nodes, nullptr, nullptr);
+}
+
+extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int by_dst,
+                              int32_t* indptr, int32_t* indices, int32_t* eid, int32_t* hub_rows,
+                              int32_t* hub_seg_ptr, int32_t* counts_host, void* ws, size_t ws_bytes,
+                              void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  STAG_CHECK_ARG(E >= 0 && N >= 0, "stag_csx_build: negative sizes");
+  STAG_CHECK_ARG(E < (1ll << 31) && N < (1ll << 31) - 1, "stag_csx_build: E and N must be < 2^31");
+  STAG_CHECK_ARG(indptr && counts_host && hub_seg_ptr, "stag_csx_build: null output");
+  STAG_CHECK_ARG(E == 0 || (src && dst && indices && eid && hub_rows), "stag_csx_build: null edge buffers");
+  if (ws_bytes < stag_csx_workspace_bytes(E, N) || !ws) {
+    set_error("stag_csx_build: workspace %zu < required %zu", ws_bytes, stag_csx_workspace_bytes(E, N));
+    return STAG_EWORKSPACE;
+  }
+  CsxWorkspace w;
+  carve(E, N, (char*)ws, &w);
+  const int64_t* key64 = by_dst ? dst : src;
+  const int64_t* other64 = by_dst ? src : dst;
+
+  uint32_t *kin = w.keys_a, *vin = w.vals_a, *kout = w.keys_b, *vout = w.vals_b;
+  if (E > 0) {
+    const int tb = 256;
+    k_init_keys<<<(unsigned)((E + tb - 1) / tb), tb, 0, stream>>>(key64, E, kin, vin);
+    STAG_LAUNCH_CHECK();
+    int bits = 1;
+    while (bits < 32 && (1ll << bits) < N) ++bits;
+    const int passes = (bits + 7) / 8;
+    for (int p = 0; p < passes; ++p) {
+      const int shift = 8 * p;
+      k_radix_hist<<<w.nblocks, RS_THREADS, 0, stream>>>(kin, E, shift, w.hist, w.nblocks);
+      STAG_LAUNCH_CHECK();
+      k_exclusive_scan<<<1, 1024, 0, stream>>>(w.hist, (int64_t)RS_RADIX * w.nblocks, nullptr);
+      STAG_LAUNCH_CHECK();
+      k_radix_scatter<<<w.nblocks, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, E, shift, w.hist, w.nblocks);
+      STAG_LAUNCH_CHECK();
+      uint32_t* t;
+      t = kin; kin = kout; kout = t;
+      t = vin; vin = vout; vout = t;
+    }
+  }
+  {
+    const int tb = 256;
+    k_indptr_from_sorted<<<(unsigned)((E + 1 + tb - 1) / tb), tb, 0, stream>>>(kin, E, N, indptr);
+    STAG_LAUNCH_CHECK();
+    if (E > 0) {
+      k_gather_other<<<(unsigned)((E + tb - 1) / tb), tb, 0, stream>>>(vin, other64, E, indices, eid);
+      STAG_LAUNCH_CHECK();
+    }
+  }
+  // hub schedule
+  int32_t counts[2] = {0, 0};
+  if (N > 0 && E > 0) {
+    const int tb = 256;
+    const unsigned gb = (unsigned)((N + tb - 1) / tb);
+    k_hub_flags<<<gb, tb, 0, stream>>>(indptr, N, w.flags_a, w.flags_b);
+    STAG_LAUNCH_CHECK();
+    k_exclusive_scan<<<1, 1024, 0, stream>>>(w.flags_a, N, w.totals);
+    STAG_LAUNCH_CHECK();
+    k_exclusive_scan<<<1, 1024, 0, stream>>>(w.flags_b, N, w.totals + 1);
+    STAG_LAUNCH_CHECK();
+    k_hub_scatter<<<gb, tb, 0, stream>>>(indptr, N, w.flags_a, w.flags_b, w.totals, hub_rows, hub_seg_ptr);
+    STAG_LAUNCH_CHECK();
+    STAG_CUDA(cudaMemcpyAsync(counts, w.totals, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  } else {
+    STAG_CUDA(cudaMemsetAsync(hub_seg_ptr, 0, sizeof(int32_t), stream));
+  }
+  STAG_CUDA(cudaStreamSynchronize(stream));
+  counts_host[0] = counts[0];
+  counts_host[1] = counts[1];
+  return STAG_OK;
+}

@@ -1,0 +1,394 @@
+"""Host-side operators over the C ABI (include/stag_b200.h).
+
+``stochastic_aggregate`` is the operator the zoo layers call where the reference
+calls ``graph.update_all(fn.u_mul_e('h','_edge_weight','m'), fn.sum('m','h'))``
+(stag/zoo/gcn.py:63,95; stag/zoo/graph_sage.py:57,72,86).  The ``edge_weight=`` slot
+of the reference's operator interface (stag/layers.py:109-113) carries either
+
+* a tensor ``[E,K]`` / ``[E,1]`` / ``[E]`` -> EXTERNAL noise (the shared-noise parity seam),
+* a :class:`NoiseSpec`                      -> noise generated inside the kernel, never stored,
+* ``None``                                  -> plain copy_u / sum.
+
+PyTorch is used for device memory, streams and autograd plumbing only; all compute
+happens in libstag_b200.so.  There is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib, random as _random
+from .graph import as_graph
+
+_KIND = {"normal": _lib.NOISE_NORMAL, "uniform": _lib.NOISE_UNIFORM, "bernoulli": _lib.NOISE_BERNOULLI}
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _require_cuda(t, what):
+    if t.device.type != "cuda":
+        raise _lib.StagLibraryError(
+            "stag_b200: %s is on %s; the stochastic aggregation runs on CUDA only (no CPU fallback)"
+            % (what, t.device))
+
+
+class NoiseSpec:
+    """Lazy description of the multiplicative edge noise of one StagLayer forward.
+
+    kind         'normal' | 'uniform' | 'bernoulli'
+    p0, p1       parameters in natural units (loc/scale, low/high, probs/None); tensors on
+                 the graph's device; may require grad (vi=True)
+    K            noise width (feat.shape[-1], 1, or base_layer.sample_dimension)
+    param_shape  'scalar' | 'channel' | 'edge' | 'edge_channel'   (before expand([E,K]))
+    relu, in_norm    stag/layers.py:98-105
+    seed, offset     Philox key / call counter (reserved at construction)
+    sample_base      global index of the first Monte-Carlo sample of this call
+    """
+
+    def __init__(self, kind, p0, p1, K, num_edges, relu=False, in_norm=False, seed=None, offset=None,
+                 sample_base=0, n_samples=1, batched=False):
+        if kind not in _KIND:
+            raise ValueError("unsupported noise kind %r" % (kind,))
+        self.kind = kind
+        self.K = int(K)
+        self.num_edges = int(num_edges)
+        self.relu = bool(relu)
+        self.in_norm = bool(in_norm)
+        self.sample_base = int(sample_base)
+        self.n_samples = int(n_samples)
+        self.batched = bool(batched)  # caller wants [S,N,D] back even when S == 1
+        if seed is None or offset is None:
+            seed, offset = _random.next_offset()
+        self.seed, self.offset = int(seed), int(offset)
+        self.p0, self.p1, self.param_shape = self._normalise(p0, p1)
+
+    def _normalise(self, p0, p1):
+        E, K = self.num_edges, self.K
+
+        def classify(p):
+            n = p.numel()
+            if n == 1:
+                return _lib.PARAM_SCALAR
+            if p.dim() >= 1 and p.shape[-1] == K and n == K and K != 1:
+                return _lib.PARAM_CHANNEL
+            if n == E and (p.dim() == 1 or p.shape[-1] == 1):
+                return _lib.PARAM_EDGE
+            if n == E * K and p.shape[-1] == K:
+                return _lib.PARAM_EDGE_CHANNEL
+            raise ValueError("noise parameter of shape %s does not expand to [E=%d, K=%d]"
+                             % (tuple(p.shape), E, K))
+
+        shapes = [classify(p) for p in (p0, p1) if p is not None]
+        shape = max(shapes)
+
+        def widen(p):
+            if p is None:
+                return None
+            if classify(p) == shape:
+                return p
+            # mixed shapes (e.g. scalar loc with per-channel scale): expand to the wider one
+            target = {_lib.PARAM_CHANNEL: (K,), _lib.PARAM_EDGE: (E, 1), _lib.PARAM_EDGE_CHANNEL: (E, K)}[shape]
+            return p.expand(target)
+
+        return widen(p0), widen(p1), shape
+
+    @property
+    def requires_grad(self):
+        return any(p is not None and p.requires_grad for p in (self.p0, self.p1))
+
+    def with_samples(self, n_samples, sample_base=0):
+        out = NoiseSpec.__new__(NoiseSpec)
+        out.__dict__.update(self.__dict__)
+        out.n_samples, out.sample_base = int(n_samples), int(sample_base)
+        return out
+
+    def materialize(self, n_samples=None, return_raw=False):
+        """The noise tensor w [E,K] (or [S,E,K]) from the same Philox stream the fused
+        kernels consume -- differentiable w.r.t. the parameters (compat path)."""
+        S = self.n_samples if n_samples is None else int(n_samples)
+        w = _NoiseEmit.apply(self, S, self.p0, self.p1)
+        if self.relu:
+            w = w.relu()
+        return w if (S > 1 or n_samples is not None) else w[0]
+
+
+def spec_samples(edge_weight, feat):
+    """``n_samples`` argument for :func:`stochastic_aggregate` implied by the edge_weight slot:
+    S for a sample-batched NoiseSpec, else None (plain [N,D] -> [N,D])."""
+    if isinstance(edge_weight, NoiseSpec) and (edge_weight.batched or feat.dim() == 3):
+        return edge_weight.n_samples
+    return None
+
+
+def _fill_noise(spec, kind, K, p0, p1, ext, relu, in_norm, sample_base, seed, offset, param_shape):
+    n = _lib.StagNoise()
+    n.kind, n.K, n.param_shape = kind, K, param_shape
+    n.relu, n.in_norm, n.sample_base = int(relu), int(in_norm), int(sample_base)
+    n.p0, n.p1, n.external = _ptr(p0), _ptr(p1), _ptr(ext)
+    n.seed, n.offset = seed, offset
+    return n
+
+
+def _c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+class _NoiseEmit(torch.autograd.Function):
+    """stag_noise_emit with reparameterisation gradients (torch reductions; compat path)."""
+
+    @staticmethod
+    def forward(ctx, spec, S, p0, p1):
+        dev = p0.device
+        _require_cuda(p0, "noise parameter")
+        lib = _lib.load()
+        E, K = spec.num_edges, spec.K
+        p0c, p1c = _c(p0), _c(p1)
+        w = torch.empty((S, E, K), dtype=torch.float32, device=dev)
+        need_raw = spec.kind != "bernoulli" and any(
+            p is not None and p.requires_grad for p in (p0, p1))
+        raw = torch.empty_like(w) if need_raw else None
+        nz = _fill_noise(spec, _KIND[spec.kind], K, p0c, p1c, None, False, False, spec.sample_base,
+                         spec.seed, spec.offset, spec.param_shape)
+        with torch.cuda.device(dev):
+            _lib.check(lib.stag_noise_emit(ctypes.byref(nz), E, S, w.data_ptr(), _ptr(raw), _stream(dev)))
+        ctx.kind = spec.kind
+        ctx.shapes = (p0.shape, None if p1 is None else p1.shape)
+        ctx.save_for_backward(raw)
+        return w
+
+    @staticmethod
+    def backward(ctx, gw):
+        (raw,) = ctx.saved_tensors
+        s0, s1 = ctx.shapes
+        g0 = g1 = None
+        if raw is not None:
+            if ctx.kind == "normal":
+                a, b = gw, gw * raw
+            else:  # uniform: w = low + u (high - low)
+                b = gw * raw
+                a = gw - b
+            if ctx.needs_input_grad[2]:
+                g0 = a.sum(0).sum_to_size(s0) if len(s0) else a.sum()
+            if ctx.needs_input_grad[3] and s1 is not None:
+                g1 = b.sum(0).sum_to_size(s1) if len(s1) else b.sum()
+        return None, None, g0, g1
+
+
+class _StochasticSpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, p0, p1, ext, cfg):
+        g = cfg["graph"]
+        st = g._s
+        dev = feat.device
+        _require_cuda(feat, "feat")
+        lib = _lib.load()
+        S, shared = cfg["S"], cfg["shared"]
+        N, D = st.num_nodes, feat.shape[-1]
+        x = _c(feat)
+        p0c, p1c, extc = _c(p0), _c(p1), _c(ext)
+        out = torch.empty((S, N, D), dtype=torch.float32, device=dev)
+        ns = None
+        if cfg["in_norm"]:
+            ns = torch.empty((S, N, cfg["K"]), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            csc, _ = st.csx(True)
+            ws_bytes = lib.stag_spmm_workspace_bytes(ctypes.byref(csc), D, S)
+            ws = st.workspace(ws_bytes)
+            nz = _fill_noise(None, cfg["kind"], cfg["K"], p0c, p1c, extc, cfg["relu"], cfg["in_norm"],
+                             cfg["sample_base"], cfg["seed"], cfg["offset"], cfg["param_shape"])
+            _lib.check(lib.stag_spmm_fwd(
+                ctypes.byref(csc), x.data_ptr(), D, 0 if shared else N * D, D, S, ctypes.byref(nz),
+                _ptr(cfg["src_scale"]), _ptr(cfg["dst_scale"]), out.data_ptr(), D, N * D,
+                _ptr(ns), ws.data_ptr(), ws.numel(), _stream(dev)))
+        ctx.cfg = cfg
+        ctx.feat_shape = feat.shape
+        ctx.param_shapes = (None if p0 is None else p0.shape, None if p1 is None else p1.shape)
+        ctx.ext_shape = None if ext is None else ext.shape
+        need_x = any(ctx.needs_input_grad[1:4])
+        ctx.save_for_backward(x if need_x else None, p0c, p1c, extc, ns)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        g = cfg["graph"]
+        st = g._s
+        x, p0c, p1c, extc, ns = ctx.saved_tensors
+        lib = _lib.load()
+        dev = gout.device
+        S, shared = cfg["S"], cfg["shared"]
+        N, D, K = st.num_nodes, gout.shape[-1], cfg["K"]
+        need_dx = ctx.needs_input_grad[0]
+        need_dp = (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and cfg["kind"] in (
+            _lib.NOISE_NORMAL, _lib.NOISE_UNIFORM)
+        need_dext = ctx.needs_input_grad[3] and cfg["kind"] == _lib.NOISE_EXTERNAL
+        gout = gout.to(torch.float32).contiguous()
+        if cfg["in_norm"]:
+            if need_dp or need_dext:
+                raise NotImplementedError(
+                    "fused gradients w.r.t. the noise through in-norm are not available; "
+                    "StagLayer routes vi=True + norm=True through the emitted-noise path")
+            gout = gout * ns  # d/d(sum) of s[v,c] * sum  (s constant w.r.t. x)
+        dx = dp0 = dp1 = dext = None
+        with torch.cuda.device(dev):
+            csr, _ = st.csx(False)
+            ws_bytes = lib.stag_spmm_workspace_bytes(ctypes.byref(csr), D, S)
+            ws = st.workspace(ws_bytes)
+            if need_dx:
+                dx = torch.empty((S, N, D), dtype=torch.float32, device=dev)
+
+            def noise(sample_base, ext_slice=None):
+                return _fill_noise(None, cfg["kind"], K, p0c, p1c, extc if ext_slice is None else ext_slice,
+                                   cfg["relu"], False, sample_base, cfg["seed"], cfg["offset"],
+                                   cfg["param_shape"])
+
+            if not (need_dp or need_dext):
+                if need_dx:
+                    # transposed aggregation only: the forward kernel on the CSR with the scales swapped
+                    nz = noise(cfg["sample_base"])
+                    _lib.check(lib.stag_spmm_fwd(
+                        ctypes.byref(csr), gout.data_ptr(), D, N * D, D, S, ctypes.byref(nz),
+                        _ptr(cfg["dst_scale"]), _ptr(cfg["src_scale"]), dx.data_ptr(), D, N * D,
+                        0, ws.data_ptr(), ws.numel(), _stream(dev)))
+            else:
+                edge_params = need_dp and cfg["param_shape"] >= _lib.PARAM_EDGE
+                if need_dext:
+                    dext = torch.empty((S, st.num_edges, K), dtype=torch.float32, device=dev)
+                if need_dp:
+                    pshape = cfg["param_shape"]
+                    n = {_lib.PARAM_SCALAR: 1, _lib.PARAM_CHANNEL: K, _lib.PARAM_EDGE: st.num_edges,
+                         _lib.PARAM_EDGE_CHANNEL: st.num_edges * K}[pshape]
+                    dp0 = torch.zeros(n, dtype=torch.float32, device=dev)
+                    dp1 = torch.zeros(n, dtype=torch.float32, device=dev)
+                # per-edge parameter gradients accumulate one sample per launch
+                groups = [(s, 1) for s in range(S)] if edge_params else [(0, S)]
+                for s0, ns_ in groups:
+                    nz = noise(cfg["sample_base"] + s0,
+                               None if extc is None else extc[s0:s0 + ns_])
+                    xs = x if shared else x[s0:s0 + ns_]
+                    _lib.check(lib.stag_spmm_bwd(
+                        ctypes.byref(csr), xs.data_ptr(), D, 0 if shared else N * D,
+                        gout[s0:s0 + ns_].data_ptr(), D, N * D, D, ns_, ctypes.byref(nz),
+                        _ptr(cfg["src_scale"]), _ptr(cfg["dst_scale"]),
+                        0 if dx is None else dx[s0:s0 + ns_].data_ptr(), D, N * D,
+                        _ptr(dp0), _ptr(dp1), 0 if dext is None else dext[s0:s0 + ns_].data_ptr(),
+                        ws.data_ptr(), ws.numel(), _stream(dev)))
+        gfeat = gp0 = gp1 = gext = None
+        if need_dx:
+            gfeat = (dx.sum(0) if shared else dx).reshape(ctx.feat_shape)
+        if need_dp:
+            s0, s1 = ctx.param_shapes
+            if ctx.needs_input_grad[1]:
+                gp0 = dp0.reshape(s0) if dp0.numel() == max(1, _numel(s0)) else dp0.reshape(-1).sum_to_size(s0)
+            if ctx.needs_input_grad[2] and s1 is not None:
+                gp1 = dp1.reshape(s1) if dp1.numel() == max(1, _numel(s1)) else dp1.reshape(-1).sum_to_size(s1)
+        if need_dext:
+            gext = dext.reshape(ctx.ext_shape) if dext.numel() == _numel(ctx.ext_shape) else dext
+        return gfeat, gp0, gp1, gext, None
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
+def stochastic_aggregate(graph, feat, edge_weight=None, reduce="sum", src_scale=None, dst_scale=None,
+                         n_samples=None):
+    """out[(s,) v, c] = dst_scale[v] * sum_{e:(u->v)} w[(s,) e, c] * (src_scale[u] * feat[(s,) u, c]).
+
+    feat ``[N,D]`` -> out ``[N,D]`` (or ``[S,N,D]`` when ``n_samples=S`` shares feat over S
+    Monte-Carlo samples); feat ``[S,N,D]`` -> out ``[S,N,D]``.  ``reduce='mean'`` divides
+    by clamp(in_degree, 1) (dgl fn.mean).
+    """
+    g = as_graph(graph)
+    st = g._s
+    N, E = st.num_nodes, st.num_edges
+    _require_cuda(feat, "feat")
+    if feat.dim() == 2:
+        shared, S = True, (1 if n_samples is None else int(n_samples))
+        squeeze = n_samples is None
+    elif feat.dim() == 3:
+        shared, S, squeeze = False, feat.shape[0], False
+        if n_samples is not None and int(n_samples) != S:
+            raise ValueError("feat has %d samples but n_samples=%s" % (S, n_samples))
+    else:
+        raise ValueError("feat must be [N,D] or [S,N,D]; got %s" % (tuple(feat.shape),))
+    if feat.shape[-2] != N:
+        raise ValueError("feat has %d rows, graph has %d nodes" % (feat.shape[-2], N))
+    D = feat.shape[-1]
+    if reduce == "mean":
+        m = st.scale(True, "inv")
+        dst_scale = m if dst_scale is None else dst_scale * m
+    elif reduce != "sum":
+        raise ValueError("reduce must be 'sum' or 'mean'")
+    cfg = {"graph": g, "S": S, "shared": shared, "relu": False, "in_norm": False, "sample_base": 0,
+           "seed": 0, "offset": 0, "param_shape": _lib.PARAM_SCALAR, "K": D,
+           "src_scale": _c(src_scale), "dst_scale": _c(dst_scale)}
+    p0 = p1 = ext = None
+    if edge_weight is None:
+        cfg["kind"] = _lib.NOISE_NONE
+    elif isinstance(edge_weight, NoiseSpec):
+        spec = edge_weight
+        if spec.num_edges != E:
+            raise ValueError("noise spec was made for %d edges, graph has %d" % (spec.num_edges, E))
+        if spec.K not in (1, D):
+            raise ValueError("noise width K=%d must be 1 or feat width %d" % (spec.K, D))
+        cfg.update(kind=_KIND[spec.kind], K=spec.K, relu=spec.relu, in_norm=spec.in_norm,
+                   sample_base=spec.sample_base, seed=spec.seed, offset=spec.offset,
+                   param_shape=spec.param_shape)
+        p0, p1 = spec.p0, spec.p1
+    else:
+        w = edge_weight
+        _require_cuda(w, "edge_weight")
+        if w.dim() == 1:
+            w = w.unsqueeze(-1)
+        K = w.shape[-1]
+        if K not in (1, D):
+            raise ValueError("edge_weight width %d must be 1 or feat width %d" % (K, D))
+        if w.dim() == 2:
+            if w.shape[0] != E:
+                raise AssertionError("edge_weight has %d rows, graph has %d edges" % (w.shape[0], E))
+            w = w.unsqueeze(0).expand(S, E, K)
+        elif w.dim() != 3 or w.shape[0] != S or w.shape[1] != E:
+            raise ValueError("edge_weight must be [E,K] or [S,E,K]; got %s" % (tuple(edge_weight.shape),))
+        cfg.update(kind=_lib.NOISE_EXTERNAL, K=K)
+        ext = w
+    out = _StochasticSpMM.apply(feat, p0, p1, ext, cfg)
+    return out[0] if squeeze else out
+
+
+def segment_reduce(graph, feat, mean=False):
+    """SumNodes / MeanNodes readout (stag/layers.py:156-178): [N,D] -> [B,D] by batch_num_nodes."""
+    return _SegmentReduce.apply(feat, as_graph(graph), bool(mean))
+
+
+class _SegmentReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, g, mean):
+        _require_cuda(feat, "feat")
+        lib = _lib.load()
+        dev = feat.device
+        x = _c(feat).reshape(feat.shape[0], -1)
+        ptr = g._s.node_ptr()
+        B, D = ptr.numel() - 1, x.shape[1]
+        out = torch.empty((B, D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.stag_segment_reduce(x.data_ptr(), D, ptr.data_ptr(), B, D, int(mean),
+                                               out.data_ptr(), D, _stream(dev)))
+        ctx.g, ctx.mean, ctx.shape = g, mean, feat.shape
+        return out.reshape((B,) + tuple(feat.shape[1:]))
+
+    @staticmethod
+    def backward(ctx, gout):
+        bnn = ctx.g.batch_num_nodes()
+        go = gout.reshape(gout.shape[0], -1)
+        if ctx.mean:
+            go = go / bnn.to(go).clamp(min=1).unsqueeze(-1)
+        return torch.repeat_interleave(go, bnn, dim=0).reshape(ctx.shape), None, None

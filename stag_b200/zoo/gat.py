@@ -1,0 +1,90 @@
+"""``GAT`` -- constructor and forward of the reference's ``stag.zoo.GAT`` (stag/zoo/gat.py:7-149).
+The noise ``[E,H]`` multiplies the pre-softmax logits (:117-119); the edge softmax is a
+different hot loop (segmented softmax) and is OUT OF SCOPE for the fused kernels
+(SURVEY.md 8(f).2): logits/softmax run as torch ops on the device, the final weighted
+aggregation ``update_all(u_mul_e('ft','a'), sum)`` (:125-126) runs on ``stag_spmm_fwd``.
+``accepts_noise_spec`` is False, so ``StagLayer`` hands this layer a tensor emitted from the
+library's Philox stream.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from ..graph import as_graph
+
+
+class GAT(nn.Module):
+    accepts_noise_spec = False
+
+    def __init__(self, in_feats, out_feats, last=False, num_heads=4, feat_drop=0.0, attn_drop=0.0,
+                 negative_slope=0.2, residual=False, activation=None, allow_zero_in_degree=False, bias=True):
+        super().__init__()
+        self._num_heads = num_heads
+        self._in_src_feats = self._in_dst_feats = in_feats
+        self._out_feats = out_feats
+        self._allow_zero_in_degree = allow_zero_in_degree
+        self.fc = nn.Linear(in_feats, out_feats * num_heads, bias=False)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.feat_drop = nn.Dropout(feat_drop)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.leaky_relu = nn.LeakyReLU(negative_slope)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(num_heads * out_feats))
+        else:
+            self.register_buffer("bias", None)
+        if residual:
+            if in_feats != out_feats * num_heads:
+                self.res_fc = nn.Linear(in_feats, num_heads * out_feats, bias=False)
+            else:
+                self.res_fc = nn.Identity()
+        else:
+            self.register_buffer("res_fc", None)
+        self.activation = activation
+        self.last = last
+        self.sample_dimension = num_heads
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_uniform_(self.fc.weight, gain=gain)
+        nn.init.xavier_uniform_(self.attn_l, gain=gain)
+        nn.init.xavier_uniform_(self.attn_r, gain=gain)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, 0)
+        if isinstance(self.res_fc, nn.Linear):
+            nn.init.xavier_uniform_(self.res_fc.weight, gain=gain)
+
+    def forward(self, graph, feat, get_attention=False, edge_weight=None):
+        g = as_graph(graph)
+        src, dst = g.edges()
+        N, H, F = g.number_of_nodes(), self._num_heads, self._out_feats
+        h = self.feat_drop(feat)
+        ft = self.fc(h).view(N, H, F)
+        el = (ft * self.attn_l).sum(dim=-1)
+        er = (ft * self.attn_r).sum(dim=-1)
+        e = self.leaky_relu(el[src] + er[dst])                     # [E,H]
+        if edge_weight is not None:
+            e = edge_weight * e
+        # segmented softmax over the in-edges of each node
+        idx = dst.unsqueeze(-1).expand_as(e)
+        mx = torch.full((N, H), float("-inf"), dtype=e.dtype, device=e.device).scatter_reduce(
+            0, idx, e, reduce="amax", include_self=True)
+        ex = torch.exp(e - mx[dst])
+        den = torch.zeros((N, H), dtype=e.dtype, device=e.device).index_add(0, dst, ex)
+        a = self.attn_drop(ex / den[dst])                          # [E,H]
+        # weighted aggregation on the fused kernel, one head at a time would waste launches:
+        # expand a to [E,H*F] lazily is E*H*F floats, so aggregate per head with K=1 weights
+        outs = [ops.stochastic_aggregate(g, ft[:, k, :].contiguous(), a[:, k:k + 1].contiguous())
+                for k in range(H)]
+        rst = torch.stack(outs, dim=1)                             # [N,H,F]
+        if self.res_fc is not None:
+            rst = rst + self.res_fc(h).view(N, -1, F)
+        if self.bias is not None:
+            rst = rst + self.bias.view(1, H, F)
+        rst = rst.mean(-2) if self.last else rst.flatten(-2, -1)
+        if self.activation:
+            rst = self.activation(rst)
+        if get_attention:
+            return rst, a.unsqueeze(-1)
+        return rst

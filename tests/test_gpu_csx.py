@@ -1,0 +1,81 @@
+"""GPU: stag_csx_build (on-device CSC/CSR builder) is bit-exact against the index oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import ref_index
+
+pytestmark = pytest.mark.gpu
+
+
+def build(src, dst, n, by_dst):
+    from stag_b200.graph import build_csx
+    g, t = build_csx(torch.from_numpy(src).cuda(), torch.from_numpy(dst).cuda(), n, by_dst)
+    torch.cuda.synchronize()
+    return g, {k: v.cpu().numpy() for k, v in t.items()}
+
+
+def check(src, dst, n, lib):
+    src, dst = np.asarray(src, np.int64), np.asarray(dst, np.int64)
+    for by_dst in (True, False):
+        g, t = build(src, dst, n, by_dst)
+        indptr, indices, eid = ref_index.csx_build(src, dst, n, by_dst)
+        assert np.array_equal(t["indptr"], indptr)
+        assert np.array_equal(t["indices"], indices)
+        assert np.array_equal(t["eid"], eid)
+        rows, segp = ref_index.hub_segments(indptr, lib.stag_hub_threshold(), lib.stag_hub_segment())
+        assert g.num_hubs == len(rows) and g.num_hub_segs == int(segp[-1])
+        assert np.array_equal(t["hub_rows"], rows)
+        assert np.array_equal(t["hub_seg_ptr"], segp)
+
+
+@pytest.mark.parametrize("n,e", [(1, 0), (1, 7), (5, 0), (3, 9), (50, 300), (257, 4096), (1000, 4097),
+                                 (70000, 300000), (169343, 1166243)])
+def test_csx_random(n, e, lib):
+    rng = np.random.default_rng(n * 31 + e)
+    check(rng.integers(0, n, e), rng.integers(0, n, e), n, lib)
+
+
+def test_csx_powerlaw_hubs(lib):
+    rng = np.random.default_rng(5)
+    n, e = 20000, 400000
+    p = 1.0 / np.arange(1, n + 1) ** 1.1
+    p /= p.sum()
+    check(rng.choice(n, e, p=p), rng.choice(n, e, p=p[::-1]), n, lib)
+
+
+def test_csx_sorted_and_reversed_input(lib):
+    n, e = 999, 50000
+    rng = np.random.default_rng(6)
+    dst = np.sort(rng.integers(0, n, e))
+    src = rng.integers(0, n, e)
+    check(src, dst, n, lib)
+    check(src, dst[::-1].copy(), n, lib)
+    check(src, np.full(e, n - 1), n, lib)  # a single row owns everything
+
+
+@pytest.mark.parametrize("name", ["t_r1_gcn", "gcn_both", "hub_d128", "powerlaw_d50"])
+def test_csx_golden_graphs(name, lib):
+    d = golden(name)
+    check(d["src"], d["dst"], int(d["num_nodes"]), lib)
+
+
+def test_degrees_and_adj_tensors(lib):
+    import stag_b200 as sb
+    d = golden("gcn_both")
+    g = sb.Graph(torch.from_numpy(d["src"]), torch.from_numpy(d["dst"]), int(d["num_nodes"])).to("cuda")
+    ind, outd = ref_index.degrees(d["src"], d["dst"], int(d["num_nodes"]))
+    assert np.array_equal(g.in_degrees().cpu().numpy(), ind)
+    assert np.array_equal(g.out_degrees().cpu().numpy(), outd)
+    indptr, indices, eid = g.adj_tensors("csc")
+    r = ref_index.csx_build(d["src"], d["dst"], int(d["num_nodes"]), True)
+    assert np.array_equal(indptr.cpu().numpy(), r[0]) and np.array_equal(eid.cpu().numpy(), r[2])
+
+
+def test_csx_rejects_bad_arguments(lib):
+    from stag_b200 import _lib
+    import ctypes
+    counts = (ctypes.c_int32 * 2)()
+    rc = lib.stag_csx_build(0, 0, -1, 4, 1, 0, 0, 0, 0, 0, counts, 0, 0, 0)
+    assert rc == _lib.STAG_EINVAL and b"negative" in lib.stag_last_error()

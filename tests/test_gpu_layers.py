@@ -1,0 +1,195 @@
+"""GPU: module-level drop-in behaviour (StagLayer / StagModel / distributions) against the
+reference-made golden vectors, plus the reference's own shape tests (stag/tests/test_layers.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.detach().cpu().double() if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a)).double()
+    b = b.detach().cpu().double() if isinstance(b, torch.Tensor) else torch.as_tensor(np.asarray(b)).double()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+# --- the reference's shape tests, on the fused path ------------------------------------------------
+def test_forward_r1():
+    import stag_b200 as stag
+    layer = stag.layers.StagLayer(stag.zoo.GCN(16, 32)).cuda()
+    g = stag.rand_graph(3, 9).to("cuda")
+    h = layer(g, torch.randn(3, 16).cuda())
+    assert h.shape == torch.Size([3, 32]) and torch.isfinite(h).all()
+    assert layer._edge_weight_sample.shape == (9, 16)
+
+
+def test_forward_rc():
+    import stag_b200 as stag
+    q_a = torch.distributions.Normal(torch.ones(16), torch.ones(16))
+    layer = stag.layers.StagLayer(stag.zoo.GCN(16, 32), q_a=q_a).cuda()
+    g = stag.rand_graph(3, 9).to("cuda")
+    assert layer(g, torch.randn(3, 16).cuda()).shape == torch.Size([3, 32])
+
+
+@pytest.mark.parametrize("outf", [1, 16])
+def test_forward_re_rec(outf):
+    import stag_b200 as stag
+    q_a = stag.distributions.AmortizedDistribution(16, outf)
+    layer = stag.layers.StagLayer(stag.zoo.GCN(16, 32), q_a=q_a).cuda()
+    g = stag.rand_graph(3, 9).to("cuda")
+    assert layer(g, torch.randn(3, 16).cuda()).shape == torch.Size([3, 32])
+
+
+def test_forward_gat_and_others():
+    import stag_b200 as stag
+    g = stag.add_self_loop(stag.rand_graph(30, 90)).to("cuda")
+    h = torch.randn(30, 16).cuda()
+    assert stag.layers.StagLayer(stag.zoo.GAT(16, 8, num_heads=4)).cuda()(g, h).shape == (30, 32)
+    assert stag.layers.StagLayer(stag.zoo.GAT(16, 8, num_heads=4, last=True)).cuda()(g, h).shape == (30, 8)
+    assert stag.layers.StagLayer(stag.zoo.GraphSAGE(16, 8)).cuda()(g, h).shape == (30, 8)
+    assert stag.layers.StagLayer(stag.zoo.GIN(16, 8)).cuda()(g, h).shape == (30, 8)
+    assert stag.layers.StagLayer(stag.zoo.GatedGCN(16, 8)).cuda()(g, h).shape == (30, 8)
+
+
+def test_fused_layer_equals_tensor_path_on_its_own_sample():
+    """The fused forward (noise never stored) equals base_layer.forward on the materialised
+    _edge_weight_sample of the same call (reference attribute, stag/layers.py:107)."""
+    import stag_b200 as stag
+    for kw in ({}, {"relu": True}, {"q_a": torch.distributions.Bernoulli(probs=0.7), "norm": True},
+               {"q_a": torch.distributions.Uniform(0.5, 1.5)}):
+        layer = stag.layers.StagLayer(stag.zoo.GCN(20, 8), **kw).cuda()
+        g = stag.rand_graph(100, 900).to("cuda")
+        h = torch.randn(100, 20).cuda()
+        out = layer(g, h)
+        w = layer._edge_weight_sample
+        assert w.shape == (900, 20)
+        ref = layer.base_layer(g, h, edge_weight=w)
+        assert rel(out, ref) < 1e-5
+
+
+# --- golden: model level -----------------------------------------------------------------------
+def _build_model_rc_vi(stag, d, **kw):
+    D0, H = d["p_0__base_layer__weight"].shape
+    C = d["p_1__base_layer__weight"].shape[1]
+    mk = lambda n: torch.distributions.Normal(torch.ones(n), torch.ones(n))  # noqa: E731
+    layers = torch.nn.ModuleList([
+        stag.layers.StagLayer(stag.zoo.GCN(D0, H, activation=torch.relu), q_a=mk(D0), p_a=mk(D0), vi=True),
+        stag.layers.StagLayer(stag.zoo.GCN(H, C, activation=lambda x: torch.softmax(x, dim=-1)), q_a=mk(H),
+                              p_a=mk(H), vi=True)])
+    sd = {k[2:].replace("__", "."): torch.from_numpy(d[k]) for k in d.files if k.startswith("p_")}
+    layers.load_state_dict(sd)   # state_dict keys identical to the reference's
+    return stag.models.StagModel(layers.cuda(), kl_scaling=float(d["kl_scaling"]), **kw), layers
+
+
+def test_model_loss_and_grads_match_reference_golden():
+    import stag_b200 as stag
+    d = golden("model_rc_vi")
+    model, layers = _build_model_rc_vi(stag, d, batch_samples=False)
+    eps = [torch.from_numpy(d["eps0"]).cuda(), torch.from_numpy(d["eps1"]).cuda()]
+    counters = [0, 0]
+    for i, layer in enumerate(layers):
+        def rsample(graph, sample_dimension, i=i, layer=layer):
+            base = layer.q_a.base_distribution
+            w = base.loc + eps[i][counters[i]] * base.scale
+            counters[i] += 1
+            return w
+        layer.rsample_noise = rsample
+    g = stag.Graph(torch.from_numpy(d["src"]), torch.from_numpy(d["dst"]), int(d["num_nodes"])).to("cuda")
+    nll, reg = model.loss_terms(g, torch.from_numpy(d["feat"]).cuda(), torch.from_numpy(d["y"]).cuda(),
+                                mask=torch.from_numpy(d["mask"]).cuda(), n_samples=eps[0].shape[0])
+    (nll + reg).backward()
+    assert rel(nll, d["nll"]) < 1e-5 and rel(reg, d["reg"]) < 1e-5
+    for k, p in layers.named_parameters():
+        assert rel(p.grad, d["g_" + k.replace(".", "__")]) < 1e-4, k
+
+
+def test_model_fused_batched_equals_sequential():
+    """S samples in one launch per layer (fused Philox, sample index = s) == S sequential passes
+    consuming the same Philox stream through the emitted-noise path."""
+    import stag_b200 as stag
+    d = golden("model_rc_vi")
+    g = stag.Graph(torch.from_numpy(d["src"]), torch.from_numpy(d["dst"]), int(d["num_nodes"])).to("cuda")
+    feat, y = torch.from_numpy(d["feat"]).cuda(), torch.from_numpy(d["y"]).cuda()
+    S = 4
+    model, layers = _build_model_rc_vi(stag, d, batch_samples=True)
+    stag.manual_seed(123)
+    loss = model.loss(g, feat, y, n_samples=S)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in layers.named_parameters()}
+    # sequential replay: layer i, sample s uses (seed, offset=i, sample=s)
+    for p in layers.parameters():
+        p.grad = None
+    total = 0.0
+    for s in range(S):
+        h = feat
+        for i, layer in enumerate(layers):
+            spec = layer.noise_spec(g, h.shape[-1])
+            spec.seed, spec.offset, spec.sample_base = 123, i, s
+            w = spec.materialize()
+            h = layer.base_layer(g, h, edge_weight=w)
+        total = total - model.likelihood.log_prob(h, y).mean()
+    reg = sum(layer.kl_divergence() for layer in layers)
+    loss2 = total / S + reg * model.kl_scaling
+    loss2.backward()
+    assert rel(loss, loss2) < 1e-5
+    for k, p in layers.named_parameters():
+        assert rel(grads[k], p.grad) < 1e-4, k
+
+
+@pytest.mark.parametrize("tag", ["re", "rec"])
+def test_amortized_matches_reference_golden(tag):
+    import stag_b200 as stag
+    d = golden("amortized_" + tag)
+    outf = d["p_q_a__parameters_mlp__loc__weight"].shape[0]
+    q_a = stag.distributions.AmortizedDistribution(16, outf)
+    layer = stag.layers.StagLayer(stag.zoo.GCN(16, 32), q_a=q_a, p_a=torch.distributions.Normal(1.0, 1.0), vi=True)
+    layer.load_state_dict({k[2:].replace("__", "."): torch.from_numpy(d[k]) for k in d.files if k.startswith("p_")})
+    layer = layer.cuda()
+    eps = torch.from_numpy(d["eps"]).cuda()
+
+    def rsample(graph, sample_dimension):
+        dist = layer.q_a.expand([graph.number_of_edges(), sample_dimension])
+        return dist.loc + eps * dist.scale
+    layer.rsample_noise = rsample
+    g = stag.Graph(torch.from_numpy(d["src"]), torch.from_numpy(d["dst"]), int(d["num_nodes"])).to("cuda")
+    feat = torch.from_numpy(d["feat"]).cuda().requires_grad_(True)
+    out = layer(g, feat)
+    kl = layer.kl_divergence()
+    ((out * torch.from_numpy(d["gout"]).cuda()).sum() + kl).backward()
+    assert rel(out, d["out"]) < 1e-5 and rel(kl, d["kl"]) < 1e-5
+    assert rel(feat.grad, d["dfeat"]) < 1e-5
+    for k, p in layer.named_parameters():
+        key = "g_" + k.replace(".", "__")
+        if key in d:
+            assert rel(p.grad, d[key]) < 1e-4, k
+
+
+def test_amortized_fused_param_grads_flow():
+    """Fused path with per-edge parameters: gradients reach the edge MLP."""
+    import stag_b200 as stag
+    q_a = stag.distributions.AmortizedDistribution(16, 16)
+    layer = stag.layers.StagLayer(stag.zoo.GCN(16, 8), q_a=q_a, vi=True).cuda()
+    g = stag.rand_graph(50, 400).to("cuda")
+    out = layer(g, torch.randn(50, 16).cuda())
+    (out.sum() + layer.kl_divergence()).backward()
+    for k, p in layer.named_parameters():
+        if k.startswith("q_a"):
+            assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0, k
+
+
+def test_mc_forward_mean_and_determinism():
+    import stag_b200 as stag
+    d = golden("model_rc_vi")
+    model, layers = _build_model_rc_vi(stag, d)
+    g = stag.Graph(torch.from_numpy(d["src"]), torch.from_numpy(d["dst"]), int(d["num_nodes"])).to("cuda")
+    feat = torch.from_numpy(d["feat"]).cuda()
+    stag.manual_seed(7)
+    a = model.forward(g, feat, n_samples=8, return_parameters=True)
+    stag.manual_seed(7)
+    b = model.forward(g, feat, n_samples=8, return_parameters=True)
+    assert torch.equal(a, b)
+    assert torch.allclose(a.sum(-1), torch.ones_like(a.sum(-1)), atol=1e-5)
+    yhat = model.forward(g, feat, n_samples=2)
+    assert yhat.shape == (int(d["num_nodes"]),)

@@ -1,0 +1,156 @@
+"""CPU: the C-ABI library loads and exports every symbol include/stag_b200.h declares; the
+host-side mirror of the reference interface (constructors, state_dict keys, error behaviour);
+no compute without a GPU -- and no CPU fallback."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "stag_b200.h")).read()
+    return sorted(set(re.findall(r"STAG_API\s+[\w\s\*]+?\b(stag_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol(lib):
+    from stag_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 12, syms
+    for s in syms:
+        assert hasattr(lib, s), "header declares %s but the library does not export it" % s
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes binding and header disagree"
+    assert lib.stag_abi_version() == 1
+    assert lib.stag_hub_threshold() > 0 and lib.stag_hub_segment() > 0
+
+
+def test_struct_layout_matches_header():
+    import ctypes
+    from stag_b200 import _lib
+    assert ctypes.sizeof(_lib.StagGraph) == 72
+    assert ctypes.sizeof(_lib.StagNoise) == 64
+
+
+def test_argument_errors_are_reported_not_thrown(lib):
+    from stag_b200 import _lib
+    import ctypes
+    g = _lib.StagGraph()
+    n = _lib.StagNoise()
+    rc = lib.stag_spmm_fwd(ctypes.byref(g), 0, 4, 0, 4, 1, ctypes.byref(n), 0, 0, 0, 4, 0, 0, 0, 0, 0)
+    assert rc == _lib.STAG_EINVAL
+    assert lib.stag_last_error()
+    assert lib.stag_noise_emit(ctypes.byref(n), 10, 1, 0, 0, 0) == _lib.STAG_EINVAL
+
+
+def test_no_cpu_fallback():
+    import stag_b200 as sb
+    g = sb.rand_graph(5, 20)
+    with pytest.raises(sb.StagLibraryError):
+        sb.ops.stochastic_aggregate(g, torch.randn(5, 8), None)
+    layer = sb.layers.StagLayer(sb.zoo.GCN(8, 4))
+    with pytest.raises(sb.StagLibraryError):
+        layer(g, torch.randn(5, 8))
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from stag_b200 import _lib
+    with pytest.raises(_lib.StagLibraryError):
+        _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_state_dict_keys_match_reference():
+    import stag_b200 as stag
+    layer = stag.layers.StagLayer(stag.zoo.GCN(16, 32))
+    assert list(layer.state_dict()) == ["base_layer.weight", "base_layer.bias", "q_a.loc", "q_a.scale",
+                                        "p_a.loc", "p_a.scale"]
+    q = torch.distributions.Normal(torch.ones(16), torch.ones(16))
+    layer = stag.layers.StagLayer(stag.zoo.GCN(16, 32), q_a=q, vi=True)
+    assert list(layer.state_dict()) == ["base_layer.weight", "base_layer.bias", "q_a.loc", "q_a.log_scale",
+                                        "p_a.loc", "p_a.log_scale"]
+    assert isinstance(layer.q_a.log_scale, torch.nn.Parameter) and layer.q_a.loc.shape == (16,)
+    assert layer.kl_divergence().item() == pytest.approx(0.0, abs=1e-7)
+    assert stag.layers.StagLayer(stag.zoo.GCN(4, 4)).kl_divergence() == 0.0
+    sage = stag.zoo.GraphSAGE(8, 4)
+    assert sorted(sage.state_dict()) == ["bias", "fc_neigh.weight", "fc_self.weight"]
+    assert sorted(stag.zoo.GraphSAGE(8, 4, aggregator_type="gcn").state_dict()) == ["bias", "fc_neigh.weight"]
+    assert stag.zoo.GAT(8, 4).sample_dimension == 4
+    assert sorted(stag.zoo.GIN(8, 4).state_dict()) == ["apply_func.bias", "apply_func.weight", "eps"]
+
+
+def test_distributions_interface():
+    """stag/tests/test_distributions.py:8-46."""
+    import stag_b200 as stag
+    D = stag.distributions
+    d = D.ParametrizedDistribution(torch.distributions.Normal(0.0, 1.0))
+    assert d.expand([10, 8]).rsample().shape == (10, 8)
+    d = D.ParametrizedDistribution(torch.distributions.Normal(0.0, 1.0), vi=True)
+    assert sorted(n for n, _ in d.named_parameters()) == ["loc", "log_scale"]
+    d = D.ParametrizedDistribution(torch.distributions.Normal(torch.zeros(10, 8), torch.ones(10, 8)))
+    assert d.expand([12, 11, 10, 8]).rsample().shape == (12, 11, 10, 8)
+    assert D.DeltaDistribution(0.0).sample() == 0.0
+    a = D.AmortizedDistribution(16, 1)
+    assert a.new_parameter_names == ["loc", "log_scale"]
+    assert d.fused_parameters()[0] == "normal"
+    assert D.ParametrizedDistribution(torch.distributions.Bernoulli(probs=0.3)).fused_parameters()[0] == "bernoulli"
+    assert D.ParametrizedDistribution(torch.distributions.Uniform(0.0, 2.0)).fused_parameters()[0] == "uniform"
+    assert D.ParametrizedDistribution(torch.distributions.Laplace(0.0, 2.0)).fused_parameters() is None
+
+
+def test_noise_spec_parameter_shape_classes():
+    from stag_b200 import _lib
+    from stag_b200.ops import NoiseSpec
+    E, K = 30, 8
+    t = torch.ones
+    assert NoiseSpec("normal", t(()), t(()), K, E, seed=0, offset=0).param_shape == _lib.PARAM_SCALAR
+    assert NoiseSpec("normal", t(K), t(K), K, E, seed=0, offset=0).param_shape == _lib.PARAM_CHANNEL
+    assert NoiseSpec("normal", t(E, 1), t(E, 1), K, E, seed=0, offset=0).param_shape == _lib.PARAM_EDGE
+    assert NoiseSpec("normal", t(E, K), t(E, K), K, E, seed=0, offset=0).param_shape == _lib.PARAM_EDGE_CHANNEL
+    s = NoiseSpec("normal", t(()), t(K), K, E, seed=0, offset=0)   # mixed -> widened
+    assert s.param_shape == _lib.PARAM_CHANNEL and s.p0.shape == (K,)
+    with pytest.raises(ValueError):
+        NoiseSpec("normal", t(5), t(5), K, E, seed=0, offset=0)
+    with pytest.raises(ValueError):
+        NoiseSpec("laplace", t(()), t(()), K, E, seed=0, offset=0)
+
+
+def test_philox_call_counter():
+    import stag_b200 as sb
+    sb.manual_seed(5)
+    a = sb.random.next_offset()
+    b = sb.random.next_offset()
+    assert a == (5, 0) and b == (5, 1)
+    sb.manual_seed(5)
+    assert sb.random.next_offset() == (5, 0)
+
+
+def test_graph_helpers_match_dgl_semantics():
+    import stag_b200 as sb
+    g = sb.Graph(torch.tensor([0, 1, 1, 2]), torch.tensor([1, 1, 2, 0]), 4)
+    assert g.number_of_nodes() == 4 and g.number_of_edges() == 4
+    assert g.in_degrees().tolist() == [1, 2, 1, 0] and g.out_degrees().tolist() == [1, 2, 1, 0]
+    s, d = sb.add_self_loop(g).edges()
+    assert s.tolist() == [0, 1, 1, 2, 0, 1, 2, 3] and d.tolist() == [1, 1, 2, 0, 0, 1, 2, 3]
+    s, d = sb.remove_self_loop(g).edges()
+    assert s.tolist() == [0, 1, 2] and d.tolist() == [1, 2, 0]
+    s, d = sb.add_reverse_edges(g).edges()
+    assert s.tolist() == [0, 1, 1, 2, 1, 1, 2, 0]
+    b = sb.batch([g, g])
+    assert b.batch_num_nodes().tolist() == [4, 4] and b.edges()[0].tolist() == [0, 1, 1, 2, 4, 5, 5, 6]
+    lv = g.local_var()
+    lv.ndata["h"] = torch.zeros(4)
+    assert "h" not in g.ndata
+    with g.local_scope():
+        g.ndata["x"] = torch.zeros(4)
+    assert "x" not in g.ndata
+
+
+def test_early_stopping_contract():
+    import stag_b200 as sb
+    es = sb.utils.EarlyStopping(patience=2)
+    m = torch.nn.Linear(2, 2)
+    assert es([1.0, 1.0], m) is False
+    assert es([0.5, 0.5], m) is False and es.best_state is not None
+    assert es([0.6, 0.6], m) is False
+    assert es([0.7, 0.7], m) is True

@@ -1,0 +1,84 @@
+"""CPU, world_size 2 over gloo: the host-side sharding logic of stag_b200.parallel (sample
+shards, flat-bucket gradient all-reduce, MC mean, row partition with halo all-gather and dX
+reduce-scatter).  The local operator is injected (the oracle), since there is no GPU here."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ref_spmm
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from stag_b200 import parallel as P
+    try:
+        # --- MC sample shards cover [0,S) exactly once --------------------------------------
+        base, n = P.shard_samples(7, rank, world)
+        got = [None] * world
+        dist.all_gather_object(got, list(range(base, base + n)))
+        assert sorted(sum(got, [])) == list(range(7))
+        assert P.shard_items(5, rank, world) == list(range(rank, 5, world))
+        # --- flat-bucket gradient averaging == mean of per-rank grads -------------------------
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(4, 3)
+        x = torch.full((2, 4), float(rank + 1))
+        lin(x).sum().backward()
+        n = P.allreduce_gradients(lin.parameters())
+        assert n == 15
+        assert torch.allclose(lin.weight.grad, torch.full((3, 4), 2 * 1.5))
+        # --- MC mean --------------------------------------------------------------------------
+        m = P.mc_mean(torch.full((3, 2), float(rank + 1)) * 2, 4)
+        assert torch.allclose(m, torch.full((3, 2), 1.5))
+        # --- row partition: halo all-gather fwd, reduce-scatter bwd == unpartitioned oracle ----
+        rng = np.random.default_rng(3)
+        N, E, D = 37, 400, 6
+        src, dst = torch.from_numpy(rng.integers(0, N, E)), torch.from_numpy(rng.integers(0, N, E))
+        X = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32))
+        W = torch.from_numpy((1 + 0.3 * rng.standard_normal((E, D))).astype(np.float32))
+        G = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32))
+        part = P.RowPartition(src, dst, N, rank, world)
+        xfull = part.gather_features(X[part.lo:part.hi].clone()).requires_grad_(True)
+        assert torch.equal(xfull.detach(), X)
+        # local aggregation over the owned destinations, noise indexed by GLOBAL edge id
+        out = ref_spmm.aggregate(part.src, part.dst, N, xfull, W[part.edge_ids])
+        own = out[part.lo:part.hi]
+        own.backward(G[part.lo:part.hi])
+        dx_block = part.scatter_gradients(xfull.grad)
+        Xo = X.clone().requires_grad_(True)
+        full = ref_spmm.aggregate(src, dst, N, Xo, W)
+        full.backward(G)
+        assert torch.allclose(own.detach(), full.detach()[part.lo:part.hi], atol=1e-6)
+        assert torch.allclose(dx_block, Xo.grad[part.lo:part.hi], atol=1e-5)
+        assert out.detach()[: part.lo].abs().sum() == 0 and out.detach()[part.hi:].abs().sum() == 0
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_row_blocks_and_sample_shards_single_process():
+    from stag_b200 import parallel as P
+    bounds, per = P.row_blocks(10, 4)
+    assert bounds == [0, 3, 6, 9, 10] and per == 3
+    assert [P.shard_samples(16, r, 8) for r in range(8)] == [(2 * r, 2) for r in range(8)]
+    assert [P.shard_samples(3, r, 4)[1] for r in range(4)] == [1, 1, 1, 0]
