@@ -172,9 +172,10 @@ class Path:
         self.gout = torch.randn((S,) + nd, device=dev, generator=gen)                   # dL/d(out of layer 3)
         self.gbuf = [torch.empty((S,) + nd, device=dev) for _ in range(2)]              # ping-pong dX
         self.dx0 = torch.empty((S,) + nd, device=dev)
-        self.loc = torch.ones(WIDTH, device=dev)
-        self.scale = torch.full((WIDTH,), SIGMA, device=dev)
-        self.dp = torch.zeros((N_LAYERS, 2, WIDTH), device=dev)
+        # q_a = Normal(1.0, std): scalar parameters expanded to [E,D] (scripts/arxiv_mle/gcn/run.py:61-62)
+        self.loc = torch.ones(1, device=dev)
+        self.scale = torch.full((1,), SIGMA, device=dev)
+        self.dp = torch.zeros((N_LAYERS, 2, 1), device=dev)
         wsb = max(self.lib.stag_spmm_workspace_bytes(ctypes.byref(self.csc), WIDTH, S),
                   self.lib.stag_spmm_workspace_bytes(ctypes.byref(self.csr), WIDTH, S))
         self.ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
@@ -184,7 +185,7 @@ class Path:
 
     def noise(self, layer):
         n = self._lib.StagNoise()
-        n.kind, n.K, n.param_shape = self._lib.NOISE_NORMAL, WIDTH, self._lib.PARAM_CHANNEL
+        n.kind, n.K, n.param_shape = self._lib.NOISE_NORMAL, WIDTH, self._lib.PARAM_SCALAR
         n.relu = n.in_norm = 0
         n.sample_base = self.sample_base
         n.p0, n.p1, n.external = self.loc.data_ptr(), self.scale.data_ptr(), 0
@@ -253,8 +254,8 @@ def e2e_leg(dev, src, dst, S, sample_base, steps, warmup, dist):
     st = g._s
     st.csx(True), st.csx(False)
     ss, ds = st.scale(False, "rsqrt"), st.scale(True, "rsqrt")
-    loc = torch.ones(WIDTH, device=dev)
-    scale = torch.full((WIDTH,), SIGMA, device=dev)
+    loc = torch.ones((), device=dev)
+    scale = torch.full((), SIGMA, device=dev)
     x_host = torch.randn(N_NODES, WIDTH).pin_memory()
     dx_host = torch.empty(N_NODES, WIDTH).pin_memory()
     obj_host = torch.empty(1).pin_memory()

@@ -84,6 +84,9 @@ typedef struct StagGraph {
   int32_t num_hub_segs;
   const int32_t* hub_rows;     /* [num_hubs]   row ids, increasing                */
   const int32_t* hub_seg_ptr;  /* [num_hubs+1] first global segment of each hub   */
+  /* processing order of the rows (decreasing stored-edge count) so that rows sharing a warp have
+   * equal trip counts; NULL = natural order.  Results do not depend on it. */
+  const int32_t* row_order;    /* [num_rows] or NULL                              */
 } StagGraph;
 
 /* Noise specification.  Parameter pointers are DEVICE pointers (they are nn.Parameters /
@@ -116,12 +119,13 @@ STAG_API int stag_hub_segment(void);
  * indptr / indices / eid against a stable sort of the COO list.
  *   hub_rows     capacity  E / stag_hub_threshold() + 1
  *   hub_seg_ptr  capacity  E / stag_hub_threshold() + 2
+ *   row_order    [N] rows by decreasing degree (optional, may be NULL)
  *   counts_host  [2] host ints: {num_hubs, num_hub_segs}  (the call synchronises `stream`)
  */
 STAG_API size_t stag_csx_workspace_bytes(int64_t num_edges, int64_t num_nodes);
 STAG_API int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes,
                    int by_dst, int32_t* indptr, int32_t* indices, int32_t* eid,
-                   int32_t* hub_rows, int32_t* hub_seg_ptr, int32_t* counts_host,
+                   int32_t* hub_rows, int32_t* hub_seg_ptr, int32_t* row_order, int32_t* counts_host,
                    void* ws, size_t ws_bytes, void* stream);
 
 /* ---- fused stochastic aggregation ------------------------------------------------------

@@ -64,8 +64,9 @@ API void ref_csx_build(const int64_t* src, const int64_t* dst, int64_t E, int64_
   free(cur);
 }
 
-static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-  for (int r = 0; r < 10; ++r) {
+#define PHILOX_ROUNDS 7
+static inline void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
     const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
@@ -79,29 +80,27 @@ static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 
-static inline float mant12(uint32_t r) {
-  union { uint32_t u; float f; } v;
-  v.u = 0x3f800000u | (r >> 9);
-  return v.f;
-}
+static inline float half_f(uint32_t h) { return (float)h; }
 
-static inline void box_muller(uint32_t ra, uint32_t rb, float* z0, float* z1) {
-  const float u = 2.0f - mant12(ra);
-  const float rad = sqrtf(-2.0f * logf(u));
-  const float ang = 6.283185307179586f * mant12(rb);
+static inline void box_muller(uint32_t r, float* z0, float* z1) {
+  const float u1 = ((float)(r & 0xffffu) + 0.5f) * 1.52587890625e-05f;
+  const float rad = sqrtf(-1.3862943611198906f * log2f(u1));
+  const float ang = fmaf(8388608.0f + (float)(r >> 16), 9.58738019107841e-05f, -804.2476806640625f);
   *z0 = rad * cosf(ang);
   *z1 = rad * sinf(ang);
 }
 
-/* raw variates of (edge, quad, sample): 4 standard normals or 4 U[0,1) */
-static inline void raw4(int kind, uint32_t e, uint32_t q, uint32_t s, uint64_t seed, uint64_t offset, float v[4]) {
+/* raw variates of (edge, oct, sample): 8 standard normals or 8 U[0,1) */
+static inline void raw8(int kind, uint32_t e, uint32_t q, uint32_t s, uint64_t seed, uint64_t offset, float v[8]) {
   uint32_t c[4] = {e, q, s, (uint32_t)(offset & 0xffffffffu)};
-  philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32));
-  if (kind == K_NORMAL) {
-    box_muller(c[0], c[1], &v[0], &v[1]);
-    box_muller(c[2], c[3], &v[2], &v[3]);
-  } else {
-    for (int i = 0; i < 4; ++i) v[i] = mant12(c[i]) - 1.0f;
+  philox4x32(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32));
+  for (int i = 0; i < 4; ++i) {
+    if (kind == K_NORMAL) {
+      box_muller(c[i], &v[2 * i], &v[2 * i + 1]);
+    } else {
+      v[2 * i] = half_f(c[i] & 0xffffu) * 1.52587890625e-05f;
+      v[2 * i + 1] = half_f(c[i] >> 16) * 1.52587890625e-05f;
+    }
   }
 }
 
@@ -119,14 +118,14 @@ API void ref_noise(int kind, int64_t E, int K, int sample, uint64_t seed, uint64
                    const float* p1, int pshape, int relu, float* w, float* raw) {
   if (K == 1 && pshape == P_CHANNEL) pshape = P_SCALAR;
   if (K == 1 && pshape == P_EDGE_CHANNEL) pshape = P_EDGE;
-  const int nq = (K + 3) / 4;
+  const int nq = (K + 7) / 8;
 #pragma omp parallel for schedule(static)
   for (int64_t e = 0; e < E; ++e) {
     for (int q = 0; q < nq; ++q) {
-      float v[4];
-      raw4(kind, (uint32_t)e, (uint32_t)q, (uint32_t)sample, seed, offset, v);
-      for (int i = 0; i < 4 && q * 4 + i < K; ++i) {
-        const int c = q * 4 + i;
+      float v[8];
+      raw8(kind, (uint32_t)e, (uint32_t)q, (uint32_t)sample, seed, offset, v);
+      for (int i = 0; i < 8 && q * 8 + i < K; ++i) {
+        const int c = q * 8 + i;
         const float a = param_at(p0, pshape, e, c, K);
         const float b = p1 ? param_at(p1, pshape, e, c, K) : 0.0f;
         float x;

@@ -7,18 +7,20 @@ torch/distributions/normal.py:82-85, uniform.py:85-88, bernoulli.py:116-119);
 bitwise parity with torch's stream is not a goal (SURVEY.md 8(c) "RNG") -- the law
 is what must agree, and tests/test_gpu_rng.py checks the law statistically.
 
-Generator: Philox4x32-10 (Salmon et al., SC'11; Random123 constants), pinned here
-against the Random123 known-answer vectors (tests/test_oracle_cpu.py).
+Generator: Philox4x32 with ROUNDS = 7 rounds (Salmon et al., SC'11; Random123 constants).
+The round function is pinned against the Random123 known-answer vectors at 10 rounds
+(tests/test_oracle_cpu.py); 7 is the smallest Crush-resistant round count (ibid., table 2).
 
-Counter / key layout (one 128-bit block = the 4 channels 4q..4q+3 of one edge):
+Counter / key layout (one 128-bit block = the 8 channels 8q..8q+7, "oct" q, of one edge):
     ctr = (eid, q, sample, offset_lo)      key = (seed_lo, seed_hi ^ offset_hi)
-Variates from the four output words r0..r3:
-    m(r)   = float32 with bits 0x3f800000 | (r >> 9)           in [1, 2)
-    uniform:   u_i = m(r_i) - 1                                in [0, 1)
-    normal :   (z0, z1) from (r0, r1), (z2, z3) from (r2, r3) by Box-Muller,
-               rad = sqrt(-2 ln(2 - m(r_a))),  ang = 2*pi*m(r_b),
-               z_even = rad * cos(ang),  z_odd = rad * sin(ang)
-    bernoulli: 1 if u_i < p else 0
+Each output word r_i (i = 0..3) gives the variates of channels 8q+2i (from its low 16 bits
+h_lo) and 8q+2i+1 (from its high 16 bits h_hi):
+    uniform  : u = h / 65536                                          in [0, 1)
+    normal   : u1 = (h_lo + 1/2) / 65536,  rad = sqrt(float32(-2 ln 2) * log2(u1))
+               ang = fma(float32(2^23 + h_hi), float32(2 pi / 65536), float32(-2 pi (128 - 2^-17)))
+                   ~ 2 pi (h_hi + 1/2) / 65536  (the fp32 fma is part of the definition)
+               z(8q+2i) = rad * cos(ang),  z(8q+2i+1) = rad * sin(ang)
+    bernoulli: 1 if u < p else 0
 A per-edge noise (K == 1) uses q = 0 and the first variate only.
 """
 import numpy as np
@@ -30,14 +32,17 @@ W1 = np.uint32(0xBB67AE85)
 MASK = np.uint64(0xFFFFFFFF)
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Vectorised Philox4x32-10.  All arguments are broadcastable uint32 arrays."""
+ROUNDS = 7
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=ROUNDS):
+    """Vectorised Philox4x32-<rounds>.  All arguments are broadcastable uint32 arrays."""
     c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3)]
     c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
     k0 = np.uint32(k0)
     k1 = np.uint32(k1)
     with np.errstate(over="ignore"):
-        for _ in range(10):
+        for _ in range(rounds):
             p0 = M0 * c0.astype(np.uint64)
             p1 = M1 * c2.astype(np.uint64)
             hi0 = (p0 >> np.uint64(32)).astype(np.uint32)
@@ -50,47 +55,45 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    return philox4x32(c0, c1, c2, c3, k0, k1, rounds=10)
+
+
 def raw_block(eid, q, sample, seed, offset):
     """The four 32-bit words for (edge, channel-quad, sample) under (seed, offset)."""
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     offset = int(offset) & 0xFFFFFFFFFFFFFFFF
     k0 = seed & 0xFFFFFFFF
     k1 = (seed >> 32) ^ (offset >> 32)
-    return philox4x32_10(eid, q, sample, np.uint32(offset & 0xFFFFFFFF), k0, k1)
+    return philox4x32(eid, q, sample, np.uint32(offset & 0xFFFFFFFF), k0, k1)
 
 
-def mant(r):
-    return ((np.asarray(r, np.uint32) >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32)
-
-
-def raw_words(num_edges, K, sample, seed, offset):
-    """uint32 [E, K] -- word used for channel c of edge e (ORIGINAL edge order)."""
-    nq = (K + 3) // 4
+def halves(num_edges, K, sample, seed, offset):
+    """uint32 [E, noct*8] -- the 16-bit integer h used for channel c of edge e (ORIGINAL edge order)."""
+    noct = (K + 7) // 8
     eid = np.arange(num_edges, dtype=np.uint32)[:, None]
-    q = np.arange(nq, dtype=np.uint32)[None, :]
-    r = raw_block(eid, q, np.uint32(sample), seed, offset)
-    return np.stack(r, axis=-1).reshape(num_edges, nq * 4)[:, :K]
+    q = np.arange(noct, dtype=np.uint32)[None, :]
+    r = np.stack(raw_block(eid, q, np.uint32(sample), seed, offset), axis=-1)      # [E, noct, 4]
+    h = np.stack([r & np.uint32(0xFFFF), r >> np.uint32(16)], axis=-1)               # [E, noct, 4, 2]
+    return h.reshape(num_edges, noct * 8)
 
 
 def uniform(num_edges, K, sample, seed, offset):
-    return mant(raw_words(num_edges, K, sample, seed, offset)) - np.float32(1.0)
+    return (halves(num_edges, K, sample, seed, offset)[:, :K].astype(np.float32) * np.float32(2.0 ** -16))
+
+
+K_ANG = np.float64(np.float32(2.0 * np.pi / 65536.0))
+C_ANG = np.float64(np.float32(-2.0 * np.pi * (128.0 - 2.0 ** -17)))
+M2LN2 = np.float64(np.float32(-2.0 * np.log(2.0)))
 
 
 def std_normal(num_edges, K, sample, seed, offset):
-    nq = (K + 3) // 4
-    eid = np.arange(num_edges, dtype=np.uint32)[:, None]
-    q = np.arange(nq, dtype=np.uint32)[None, :]
-    r0, r1, r2, r3 = raw_block(eid, q, np.uint32(sample), seed, offset)
-
-    def bm(ra, rb):
-        u = (np.float32(2.0) - mant(ra)).astype(np.float64)
-        rad = np.sqrt(-2.0 * np.log(u))
-        ang = 2.0 * np.pi * mant(rb).astype(np.float64)
-        return rad * np.cos(ang), rad * np.sin(ang)
-
-    z0, z1 = bm(r0, r1)
-    z2, z3 = bm(r2, r3)
-    z = np.stack([z0, z1, z2, z3], axis=-1).reshape(num_edges, nq * 4)[:, :K]
+    noct = (K + 7) // 8
+    h = halves(num_edges, K, sample, seed, offset).reshape(num_edges, noct * 4, 2).astype(np.float64)
+    u1 = (h[..., 0] + 0.5) * 2.0 ** -16
+    rad = np.sqrt(M2LN2 * np.log2(u1))
+    ang = np.float32((8388608.0 + h[..., 1]) * K_ANG + C_ANG).astype(np.float64)   # exact fp32 fma
+    z = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=-1).reshape(num_edges, noct * 8)[:, :K]
     return z.astype(np.float32)
 
 

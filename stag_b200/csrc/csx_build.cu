@@ -173,6 +173,24 @@ __global__ void k_hub_scatter(const int32_t* __restrict__ indptr, int64_t N, con
   if (v == 0) hub_seg_ptr[totals[0]] = (int32_t)totals[1];
 }
 
+// row processing order: rows sorted by decreasing stored-edge count (ties: decreasing row id), so
+// that the rows sharing a warp -- and the warps sharing a CTA -- have equal trip counts.  Hub rows
+// (handled as segments) all carry the same clamped key.
+__global__ void k_degree_keys(const int32_t* __restrict__ indptr, int64_t N, uint32_t* __restrict__ keys,
+                              uint32_t* __restrict__ vals) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N) {
+    const int deg = indptr[v + 1] - indptr[v];
+    keys[v] = (uint32_t)min(deg, kHubThreshold + 1);
+    vals[v] = (uint32_t)v;
+  }
+}
+
+__global__ void k_reverse_order(const uint32_t* __restrict__ sorted_rows, int64_t N, int32_t* __restrict__ row_order) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) row_order[i] = (int32_t)sorted_rows[N - 1 - i];
+}
+
 struct CsxWorkspace {
   uint32_t *keys_a, *vals_a, *keys_b, *vals_b, *hist, *flags_a, *flags_b, *totals;
   int nblocks;
@@ -185,8 +203,9 @@ static size_t carve(int64_t E, int64_t N, char* base, CsxWorkspace* w) {
     off += align_up(bytes, 256);
     return (uint32_t*)p;
   };
-  const int nblocks = (int)((E + RS_TILE - 1) / RS_TILE);
-  const size_t e = (size_t)(E > 0 ? E : 1);
+  const int64_t M = E > N ? E : N;  // the same buffers sort the E edges and, later, the N rows
+  const int nblocks = (int)((M + RS_TILE - 1) / RS_TILE);
+  const size_t e = (size_t)(M > 0 ? M : 1);
   CsxWorkspace tmp;
   tmp.nblocks = nblocks;
   tmp.keys_a = take(e * 4);
@@ -211,8 +230,8 @@ extern "C" size_t stag_csx_workspace_bytes(int64_t num_edges, int64_t num_nodes)
 
 extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int by_dst,
                               int32_t* indptr, int32_t* indices, int32_t* eid, int32_t* hub_rows,
-                              int32_t* hub_seg_ptr, int32_t* counts_host, void* ws, size_t ws_bytes,
-                              void* stream_) {
+                              int32_t* hub_seg_ptr, int32_t* row_order, int32_t* counts_host, void* ws,
+                              size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   STAG_CHECK_ARG(E >= 0 && N >= 0, "stag_csx_build: negative sizes");
   STAG_CHECK_ARG(E < (1ll << 31) && N < (1ll << 31) - 1, "stag_csx_build: E and N must be < 2^31");
@@ -235,13 +254,14 @@ extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E,
     int bits = 1;
     while (bits < 32 && (1ll << bits) < N) ++bits;
     const int passes = (bits + 7) / 8;
+    const int eb = (int)((E + RS_TILE - 1) / RS_TILE);
     for (int p = 0; p < passes; ++p) {
       const int shift = 8 * p;
-      k_radix_hist<<<w.nblocks, RS_THREADS, 0, stream>>>(kin, E, shift, w.hist, w.nblocks);
+      k_radix_hist<<<eb, RS_THREADS, 0, stream>>>(kin, E, shift, w.hist, eb);
       STAG_LAUNCH_CHECK();
-      k_exclusive_scan<<<1, 1024, 0, stream>>>(w.hist, (int64_t)RS_RADIX * w.nblocks, nullptr);
+      k_exclusive_scan<<<1, 1024, 0, stream>>>(w.hist, (int64_t)RS_RADIX * eb, nullptr);
       STAG_LAUNCH_CHECK();
-      k_radix_scatter<<<w.nblocks, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, E, shift, w.hist, w.nblocks);
+      k_radix_scatter<<<eb, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, E, shift, w.hist, eb);
       STAG_LAUNCH_CHECK();
       uint32_t* t;
       t = kin; kin = kout; kout = t;
@@ -256,6 +276,22 @@ extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E,
       k_gather_other<<<(unsigned)((E + tb - 1) / tb), tb, 0, stream>>>(vin, other64, E, indices, eid);
       STAG_LAUNCH_CHECK();
     }
+  }
+  // row processing order: one 8-bit stable radix pass over the clamped degrees
+  if (row_order && N > 0) {
+    const int tb = 256;
+    const unsigned gb = (unsigned)((N + tb - 1) / tb);
+    const int nb = (int)((N + RS_TILE - 1) / RS_TILE);
+    k_degree_keys<<<gb, tb, 0, stream>>>(indptr, N, w.keys_a, w.vals_a);
+    STAG_LAUNCH_CHECK();
+    k_radix_hist<<<nb, RS_THREADS, 0, stream>>>(w.keys_a, N, 0, w.hist, nb);
+    STAG_LAUNCH_CHECK();
+    k_exclusive_scan<<<1, 1024, 0, stream>>>(w.hist, (int64_t)RS_RADIX * nb, nullptr);
+    STAG_LAUNCH_CHECK();
+    k_radix_scatter<<<nb, RS_THREADS, 0, stream>>>(w.keys_a, w.vals_a, w.keys_b, w.vals_b, N, 0, w.hist, nb);
+    STAG_LAUNCH_CHECK();
+    k_reverse_order<<<gb, tb, 0, stream>>>(w.vals_b, N, row_order);
+    STAG_LAUNCH_CHECK();
   }
   // hub schedule
   int32_t counts[2] = {0, 0};

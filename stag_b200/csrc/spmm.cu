@@ -4,7 +4,7 @@
 // writing the [E,K] noise tensor to HBM:
 //   counter-based Philox noise -> reparameterisation (loc/scale, low/high, probs) -> relu
 //   -> message scaling -> segmented reduction (+ in-norm, + degree scalings)
-// and, in the backward instantiation, the transposed aggregation (dX) together with the
+// and, in the gradient instantiation, the transposed aggregation (dX) together with the
 // SDDMM term reduced straight into the noise-parameter gradients.
 //
 // Reference path replaced (file:line in /root/reference):
@@ -14,11 +14,21 @@
 //   degree scalings                stag/zoo/gcn.py:67-75,100-108
 //   autograd of the above          DGL GSpMM.backward (gspmm on the reverse graph + gsddmm)
 //
-// Mapping: a row (destination node for CSC, source node for CSR) is owned by a group of
-// LPR lanes (LPR = 32 for D >= 128; narrower rows pack 32/LPR rows into a warp); each lane
-// owns one channel quad, i.e. one 128-bit feature load and one Philox block per edge.
+// Mapping: a row (destination node for CSC, source node for CSR) is owned by a group of LPR
+// lanes; each lane owns one OCT of channels (8 floats = two 128-bit loads = one Philox block
+// per edge).  D = 128 -> LPR = 16, two rows per warp; narrower rows pack more rows per warp,
+// wider rows loop over channel chunks.  The group first loads up to LPR edge records
+// (neighbour id, edge id, gather scale, and for per-edge noise the weight itself) with one
+// coalesced load per lane and then broadcasts them edge by edge with shuffles.
 // Rows longer than kHubThreshold are cut into segments that are scheduled as independent
 // work items and combined in a fixed order by a finalize kernel (deterministic).
+//
+// MODE 0  per-edge scalar weight (none / external [E,1] / generated K == 1): folded into the
+//         broadcast scale, the inner loop is 2 x LDG.128 + 8 FFMA
+// MODE 1  external per-channel weights [E,K] read from memory (the shared-noise parity seam)
+// MODE 2  per-channel noise generated in registers; PSH 0: scalar or per-edge parameters
+//         (travel with the edge record, folded with the gather scale), 1: per-channel
+//         parameters in registers, 2: per-edge-per-channel parameters read from memory
 #include "common.cuh"
 #include "noise.cuh"
 
@@ -26,7 +36,6 @@ namespace stag {
 
 constexpr int AGG_THREADS = 256;
 constexpr int AGG_WARPS = AGG_THREADS / 32;
-constexpr int AGG_UNROLL = 4;
 
 struct AggParams {
   // structure
@@ -35,6 +44,7 @@ struct AggParams {
   const int32_t* eid;
   const int32_t* hub_rows;
   const int32_t* hub_seg_ptr;
+  const int32_t* row_order;  // rows in processing order (by degree), or null
   int num_hubs, num_hub_segs;
   int N;
   int64_t E;
@@ -45,16 +55,20 @@ struct AggParams {
   const float* rscale;
   float* out;
   int64_t ldo, out_ss;
-  int D, S, nq;
+  int D, S, noct;
   int lpr_log2;
+  // column blocks: the channels are processed in ncb blocks of cw floats so that the gathered
+  // operand of one block ([N, cw]) stays L2-resident; cb_major orders the blocks outermost
+  // (operand shared by all samples), otherwise the samples are outermost
+  int ncb, cw, cb_major;
   // noise
-  int K, pshape, relu, in_norm, sample_base;
+  int kind, K, pshape, relu, in_norm, sample_base;
   const float* p0;
   const float* p1;
   const float* ext;
   PhiloxKey key;
   float* norm_scale_out;
-  // hub partial sums [S][num_hub_segs][nq*4]
+  // hub partial sums [S][num_hub_segs][noct*8]
   float* part_acc;
   float* part_w;
   // gradient mode
@@ -63,86 +77,41 @@ struct AggParams {
   float* dp0;
   float* dp1;
   float* dw_ext;
-  float* dp_partial;  // [grid][2][nq*4]
+  float* dp_partial;  // [grid][2][noct*8]
 };
 
-__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-
-template <bool ALIGNED>
-__device__ __forceinline__ float4 load4(const float* __restrict__ row, int c, int D) {
-  if (ALIGNED) {
-    return __ldg(reinterpret_cast<const float4*>(row + c));
+template <bool VEC>
+__device__ __forceinline__ void load8(const float* __restrict__ row, int c, int D, float (&v)[8]) {
+  if (VEC) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (c < D) a = __ldg(reinterpret_cast<const float4*>(row + c));
+    if (c + 4 < D) b = __ldg(reinterpret_cast<const float4*>(row + c + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
-    float4 v = f4zero();
-    if (c + 0 < D) v.x = __ldg(row + c + 0);
-    if (c + 1 < D) v.y = __ldg(row + c + 1);
-    if (c + 2 < D) v.z = __ldg(row + c + 2);
-    if (c + 3 < D) v.w = __ldg(row + c + 3);
-    return v;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (c + i < D) ? __ldg(row + c + i) : 0.f;
   }
 }
 
-template <bool ALIGNED>
-__device__ __forceinline__ void store4(float* __restrict__ row, int c, int D, float4 v) {
-  if (ALIGNED) {
-    *reinterpret_cast<float4*>(row + c) = v;
-  } else {
-    if (c + 0 < D) row[c + 0] = v.x;
-    if (c + 1 < D) row[c + 1] = v.y;
-    if (c + 2 < D) row[c + 2] = v.z;
-    if (c + 3 < D) row[c + 3] = v.w;
-  }
-}
-
-__device__ __forceinline__ float4 bcast4(float v) { return make_float4(v, v, v, v); }
-
-// Parameter quad for (edge e, channel c).  pshape EDGE* are read per edge.
-template <bool ALIGNED>
-__device__ __forceinline__ float4 edge_param(const float* __restrict__ p, int pshape, int K, int64_t e, int c) {
-  if (pshape == STAG_PARAM_EDGE || K == 1) return bcast4(__ldg(p + e));
-  return load4<ALIGNED>(p + e * (int64_t)K, c, K);
-}
-
-// Noise quad for one (edge, quad, sample).  `raw` returns the un-transformed variate
-// (standard normal / uniform) and `pre` the value before relu; both are only needed by
-// the gradient instantiation.
-template <int KIND, bool ALIGNED>
-__device__ __forceinline__ float4 noise_quad(const AggParams& p, int64_t e, int c, int s_local,
-                                             const float4& P0, const float4& P1, float4& raw, float4& pre) {
-  float4 w;
-  if (KIND == STAG_NOISE_NONE) {
-    w = bcast4(1.0f);
-    raw = w;
-    pre = w;
-    return w;
-  }
-  if (KIND == STAG_NOISE_EXTERNAL) {
-    const float* base = p.ext + (int64_t)s_local * p.E * p.K;
-    if (p.K == 1) w = bcast4(__ldg(base + e));
-    else w = load4<ALIGNED>(base + e * (int64_t)p.K, c, p.K);
-    raw = w;
-  } else {
-    const uint32_t q = p.K == 1 ? 0u : (uint32_t)(c >> 2);
-    raw = raw_variates<KIND>((uint32_t)e, q, (uint32_t)(p.sample_base + s_local), p.key);
-    if (p.K == 1) raw = bcast4(raw.x);
-    float4 a = P0, b = P1;
-    if (p.pshape >= STAG_PARAM_EDGE) {
-      a = edge_param<ALIGNED>(p.p0, p.pshape, p.K, e, c);
-      if (KIND != STAG_NOISE_BERNOULLI) b = edge_param<ALIGNED>(p.p1, p.pshape, p.K, e, c);
+// STREAM: evict-first store for the big output stream, so that it does not push the gathered
+// operand out of L2
+template <bool VEC, bool STREAM>
+__device__ __forceinline__ void store8(float* __restrict__ row, int c, int D, const float (&v)[8]) {
+  if (VEC) {
+    const float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
+    if (STREAM) {
+      if (c < D) __stcs(reinterpret_cast<float4*>(row + c), a);
+      if (c + 4 < D) __stcs(reinterpret_cast<float4*>(row + c + 4), b);
+    } else {
+      if (c < D) *reinterpret_cast<float4*>(row + c) = a;
+      if (c + 4 < D) *reinterpret_cast<float4*>(row + c + 4) = b;
     }
-    w.x = transform<KIND>(raw.x, a.x, b.x);
-    w.y = transform<KIND>(raw.y, a.y, b.y);
-    w.z = transform<KIND>(raw.z, a.z, b.z);
-    w.w = transform<KIND>(raw.w, a.w, b.w);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (c + i < D) row[c + i] = v[i];
   }
-  pre = w;
-  if (p.relu) {
-    w.x = fmaxf(w.x, 0.f);
-    w.y = fmaxf(w.y, 0.f);
-    w.z = fmaxf(w.z, 0.f);
-    w.w = fmaxf(w.w, 0.f);
-  }
-  return w;
 }
 
 __device__ __forceinline__ float group_sum(float v, int lpr) {
@@ -150,34 +119,85 @@ __device__ __forceinline__ float group_sum(float v, int lpr) {
   return v;
 }
 
-template <int KIND, bool ALIGNED, bool GRADS>
-__global__ void __launch_bounds__(AGG_THREADS) agg_kernel(const AggParams p) {
-  extern __shared__ float smem[];  // GRADS: [AGG_WARPS][2][nq*4]
+__device__ __forceinline__ float sum8(const float (&v)[8]) {
+  return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+}
+
+// Hot path of MODE 2 / PSH 0 without relu / in-norm / gradients: the weights of one oct with the
+// gather scale already folded into the two per-edge values (A, B) by the lane that loaded the
+// edge record:   NORMAL  A = sc*loc, B = sc*scale      w*sc = A + B*eps
+//                UNIFORM A = sc*low, B = sc*(high-low)  w*sc = A + B*u
+//                BERNOULLI A = p,    B = sc             w*sc = u < A ? B : 0
+template <int KIND>
+__device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t smp, const PhiloxKey& key, float A,
+                                           float B, float (&w)[8]) {
+  const uint4 r = philox4x32<kPhiloxRounds>(eid, oct, smp, key.c3, key.k0, key.k1);
+  const uint32_t q[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (KIND == STAG_NOISE_NORMAL) {
+      float rad, c, s;
+      bm_parts(q[i], rad, c, s);
+      const float rb = rad * B;
+      w[2 * i] = fmaf(c, rb, A);
+      w[2 * i + 1] = fmaf(s, rb, A);
+    } else if (KIND == STAG_NOISE_UNIFORM) {
+      w[2 * i] = fmaf(half_uniform<false>(q[i]), B, A);
+      w[2 * i + 1] = fmaf(half_uniform<true>(q[i]), B, A);
+    } else {
+      w[2 * i] = half_uniform<false>(q[i]) < A ? B : 0.f;
+      w[2 * i + 1] = half_uniform<true>(q[i]) < A ? B : 0.f;
+    }
+  }
+}
+
+template <int MODE, int KIND, int PSH, bool VEC, bool GRADS, bool FOLD>
+__global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const AggParams p) {
+  extern __shared__ float smem[];  // param grads: [AGG_WARPS][2][noct*8]
+  constexpr int U = GRADS ? 1 : 2;  // edges in flight per lane
+  constexpr bool GEN = MODE == 2;
+  // parameter gradients exist for generated Normal / Uniform noise only
+  constexpr bool PGRADS_C = GRADS && GEN && (KIND == STAG_NOISE_NORMAL || KIND == STAG_NOISE_UNIFORM);
+  const bool pgrads_e = GRADS && MODE == 0 && (p.kind == STAG_NOISE_NORMAL || p.kind == STAG_NOISE_UNIFORM);
+  const bool dense_pg = (PGRADS_C || pgrads_e) && p.pshape <= STAG_PARAM_CHANNEL;  // reduced to [1] / [K]
+  // FOLD (hot path: MODE 2 / PSH 0 without relu / in-norm / gradients): the gather scale is folded
+  // into the per-edge parameters
+  constexpr bool fold = FOLD;
+
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int LPR = 1 << p.lpr_log2;
   const int RPW = 32 >> p.lpr_log2;
   const int sub = lane >> p.lpr_log2;
   const int sl = lane & (LPR - 1);
-  const int nq4 = p.nq * 4;
-  constexpr bool PARAM_GRADS = GRADS && (KIND == STAG_NOISE_NORMAL || KIND == STAG_NOISE_UNIFORM);
+  const int D8 = p.noct * 8;
 
   float* my_sm = nullptr;
-  if (PARAM_GRADS) {
-    my_sm = smem + (size_t)warp * 2 * nq4;
-    for (int i = lane; i < 2 * nq4; i += 32) my_sm[i] = 0.f;
+  if (GRADS && dense_pg) {
+    my_sm = smem + (size_t)warp * 2 * D8;
+    for (int i = lane; i < 2 * D8; i += 32) my_sm[i] = 0.f;
     __syncwarp();
   }
 
   const int HG = (p.num_hub_segs + RPW - 1) / RPW;
   const int RG = (p.N + RPW - 1) / RPW;
   const int64_t per_sample = (int64_t)HG + RG;
-  const int64_t total = per_sample * p.S;
+  const int64_t total = per_sample * p.S * p.ncb;
   const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
 
   for (int64_t item = (int64_t)blockIdx.x * AGG_WARPS + warp; item < total; item += total_warps) {
-    const int s = (int)(item / per_sample);
-    const int r = (int)(item - (int64_t)s * per_sample);
+    const int64_t outer = item / per_sample;
+    const int r = (int)(item - outer * per_sample);
+    int s, cb;
+    if (p.cb_major) {
+      cb = (int)(outer / p.S);
+      s = (int)(outer - (int64_t)cb * p.S);
+    } else {
+      s = (int)(outer / p.ncb);
+      cb = (int)(outer - (int64_t)s * p.ncb);
+    }
+    const int c_begin = cb * p.cw;
+    const int c_end = min(c_begin + p.cw, D8);
     // resolve this lane-group's row and edge range
     int row = -1, beg = 0, len = 0, part_slot = -1;
     if (r < HG) {
@@ -196,8 +216,9 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_kernel(const AggParams p) {
         part_slot = seg;
       }
     } else {
-      const int v = (r - HG) * RPW + sub;
-      if (v < p.N) {
+      const int vi = (r - HG) * RPW + sub;
+      if (vi < p.N) {
+        const int v = p.row_order ? __ldg(p.row_order + vi) : vi;
         const int rb = __ldg(p.indptr + v), re = __ldg(p.indptr + v + 1);
         if (re - rb <= kHubThreshold) {
           row = v;
@@ -209,118 +230,240 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_kernel(const AggParams p) {
     int maxlen = len;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-    int anyrow = row >= 0;
-    anyrow = __any_sync(0xffffffffu, anyrow);
-    if (!anyrow) continue;
+    if (!__any_sync(0xffffffffu, row >= 0)) continue;
 
     const float* xs = p.x + (int64_t)s * p.x_ss;
     const float rs = (row >= 0 && p.rscale) ? __ldg(p.rscale + row) : 1.0f;
+    const uint32_t smp = (uint32_t)(p.sample_base + s);
 
-    for (int c0 = 0; c0 < nq4; c0 += LPR * 4) {
-      const int c = c0 + sl * 4;
-      const bool qvalid = c < p.D;
-      float4 P0 = f4zero(), P1 = f4zero();
-      if (KIND >= STAG_NOISE_NORMAL && p.pshape <= STAG_PARAM_CHANNEL) {
-        if (p.pshape == STAG_PARAM_SCALAR || p.K == 1) {
-          P0 = bcast4(__ldg(p.p0));
-          if (p.p1) P1 = bcast4(__ldg(p.p1));
-        } else if (qvalid) {
-          P0 = load4<ALIGNED>(p.p0, c, p.D);
-          if (p.p1) P1 = load4<ALIGNED>(p.p1, c, p.D);
-        }
+    for (int c0 = c_begin; c0 < c_end; c0 += LPR * 8) {
+      const int c = c0 + sl * 8;
+      const bool qvalid = c < p.D && c < c_end;
+      const uint32_t oct = (uint32_t)(c >> 3);
+      float P0[8], P1[8];
+      if (GEN && PSH == 1) {
+        load8<VEC>(p.p0, c, p.D, P0);
+        if (KIND != STAG_NOISE_BERNOULLI) load8<VEC>(p.p1, c, p.D, P1);
       }
-      float4 acc = f4zero(), wsum = f4zero();
-      float4 xr = f4zero(), d0 = f4zero(), d1 = f4zero();
+      float acc[8], wsum[8], xr[8], d0[8], d1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = wsum[i] = d0[i] = d1[i] = xr[i] = 0.f;
+      float wsum_e = 0.f;  // MODE 0 in-norm: sum of the per-edge weights of this row
+      float d0_e = 0.f, d1_e = 0.f;
       if (GRADS && row >= 0 && qvalid) {
-        xr = load4<ALIGNED>(p.xrow + (int64_t)s * p.xr_ss + (int64_t)row * p.ldxr, c, p.D);
-        xr.x *= rs; xr.y *= rs; xr.z *= rs; xr.w *= rs;
+        load8<VEC>(p.xrow + (int64_t)s * p.xr_ss + (int64_t)row * p.ldxr, c, p.D, xr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xr[i] *= rs;
       }
 
       for (int off = 0; off < maxlen; off += LPR) {
+        // ---- edge records of this batch: lane sl owns edge off + sl ---------------------------
+        //   MODE 0        my_a = gather scale * weight, my_b = weight
+        //   MODE 2 PSH 0  my_a / my_b = the two parameters (folded with the gather scale if `fold`)
         int my_idx = 0, my_eid = 0;
-        float my_sc = 0.f;
+        float my_sc = 0.f, my_a = 0.f, my_b = 0.f, my_raw = 0.f, my_pre = 0.f;
         if (off + sl < len) {
           my_idx = __ldg(p.indices + beg + off + sl);
           my_eid = __ldg(p.eid + beg + off + sl);
           my_sc = p.gscale ? __ldg(p.gscale + my_idx) : 1.0f;
+          if (MODE == 0) {
+            float w = 1.0f;
+            if (p.kind == STAG_NOISE_EXTERNAL) {
+              w = __ldg(p.ext + (int64_t)s * p.E + my_eid);
+              my_raw = w;
+            } else if (p.kind >= STAG_NOISE_NORMAL) {
+              const int64_t pi = p.pshape >= STAG_PARAM_EDGE ? my_eid : 0;
+              const float a = __ldg(p.p0 + pi);
+              const float b = p.p1 ? __ldg(p.p1 + pi) : 0.f;
+              my_raw = raw_first(p.kind, (uint32_t)my_eid, smp, p.key);
+              w = transform_rt(p.kind, my_raw, a, b);
+            }
+            my_pre = w;
+            if (p.relu) w = fmaxf(w, 0.f);
+            my_b = w;
+            my_a = my_sc * w;
+          } else if (GEN && PSH == 0) {
+            const int64_t pi = p.pshape >= STAG_PARAM_EDGE ? my_eid : 0;
+            const float a = __ldg(p.p0 + pi);
+            const float b = KIND != STAG_NOISE_BERNOULLI ? __ldg(p.p1 + pi) : 0.f;
+            if (fold) {
+              if (KIND == STAG_NOISE_NORMAL) { my_a = my_sc * a; my_b = my_sc * b; }
+              else if (KIND == STAG_NOISE_UNIFORM) { my_a = my_sc * a; my_b = my_sc * (b - a); }
+              else { my_a = a; my_b = my_sc; }
+            } else {
+              my_a = a;
+              my_b = b;
+            }
+          }
         }
-        const int cntmax = min(LPR, maxlen - off);
-        for (int t0 = 0; t0 < cntmax; t0 += AGG_UNROLL) {
-          float4 xv[AGG_UNROLL];
-          int ee[AGG_UNROLL];
-          float sc[AGG_UNROLL];
-          bool act[AGG_UNROLL];
+        const int cnt = min(LPR, maxlen - off);
+        for (int t0 = 0; t0 < cnt; t0 += U) {
+          float xv[U][8];
+          int ee[U];
+          float sa[U], sb[U], ssc[U];
+          bool act[U];
 #pragma unroll
-          for (int k = 0; k < AGG_UNROLL; ++k) {
+          for (int k = 0; k < U; ++k) {
             const int t = t0 + k;
             const int u = __shfl_sync(0xffffffffu, my_idx, t, LPR);
             ee[k] = __shfl_sync(0xffffffffu, my_eid, t, LPR);
-            sc[k] = __shfl_sync(0xffffffffu, my_sc, t, LPR);
+            ssc[k] = __shfl_sync(0xffffffffu, my_sc, t, LPR);
+            sa[k] = 0.f;
+            sb[k] = 0.f;
+            if (MODE == 0 || (GEN && PSH == 0)) {
+              sa[k] = __shfl_sync(0xffffffffu, my_a, t, LPR);
+              sb[k] = __shfl_sync(0xffffffffu, my_b, t, LPR);
+            }
             act[k] = (t < LPR) && (off + t < len) && qvalid;
-            xv[k] = act[k] ? load4<ALIGNED>(xs + (int64_t)u * p.ldx, c, p.D) : f4zero();
+            if (act[k]) {
+              load8<VEC>(xs + (int64_t)u * p.ldx, c, p.D, xv[k]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xv[k][i] = 0.f;
+            }
           }
 #pragma unroll
-          for (int k = 0; k < AGG_UNROLL; ++k) {
-            if (t0 + k >= cntmax) break;  // warp-uniform
-            float4 raw, pre;
-            float4 w = f4zero();
-            if (act[k]) w = noise_quad<KIND, ALIGNED>(p, ee[k], c, s, P0, P1, raw, pre);
-            else { raw = f4zero(); pre = f4zero(); }
-            const float4 g = make_float4(xv[k].x * sc[k], xv[k].y * sc[k], xv[k].z * sc[k], xv[k].w * sc[k]);
-            acc.x = fmaf(w.x, g.x, acc.x);
-            acc.y = fmaf(w.y, g.y, acc.y);
-            acc.z = fmaf(w.z, g.z, acc.z);
-            acc.w = fmaf(w.w, g.w, acc.w);
-            if (!GRADS) {
-              wsum.x += w.x; wsum.y += w.y; wsum.z += w.z; wsum.w += w.w;
+          for (int k = 0; k < U; ++k) {
+            if (t0 + k >= cnt) break;  // warp-uniform
+            const bool edge_ok = (t0 + k < LPR) && (off + t0 + k < len);
+            if (MODE == 0) {
+              // -------- per-edge weight ------------------------------------------------------
+              if (!GRADS) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv[k][i], sa[k], acc[i]);
+                if (edge_ok) wsum_e += sb[k];
+              } else {
+                float dwc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float g = xv[k][i] * ssc[k];
+                  acc[i] = fmaf(sb[k], g, acc[i]);
+                  dwc[i] = xr[i] * g;
+                }
+                if (p.kind != STAG_NOISE_NONE && (p.dw_ext || pgrads_e)) {
+                  const float tot = group_sum(sum8(dwc), LPR);
+                  const float raw = __shfl_sync(0xffffffffu, my_raw, t0 + k, LPR);
+                  const float pre = __shfl_sync(0xffffffffu, my_pre, t0 + k, LPR);
+                  if (sl == 0 && edge_ok) {
+                    if (p.kind == STAG_NOISE_EXTERNAL) {
+                      if (p.dw_ext) {
+                        float* base = p.dw_ext + (int64_t)s * p.E;
+                        // several channel chunks accumulate into the same slot, from the same thread
+                        if (c0 == c_begin) base[ee[k]] = tot; else base[ee[k]] += tot;
+                      }
+                    } else if (pgrads_e) {
+                      const float e = (p.relu && !(pre > 0.f)) ? 0.f : tot;
+                      const float e1 = e * raw;
+                      const float e0 = p.kind == STAG_NOISE_NORMAL ? e : e - e1;
+                      if (p.pshape <= STAG_PARAM_CHANNEL) {
+                        d0_e += e0;
+                        d1_e += e1;
+                      } else {
+                        p.dp0[ee[k]] += e0;
+                        p.dp1[ee[k]] += e1;
+                      }
+                    }
+                  }
+                }
+              }
+            } else if (fold) {
+              // -------- generated per-channel noise, hot path ------------------------------------
+              float w[8];
+              folded_oct<KIND>((uint32_t)ee[k], oct, smp, p.key, sa[k], sb[k], w);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] = fmaf(w[i], xv[k][i], acc[i]);
             } else {
-              float4 dw = make_float4(xr.x * g.x, xr.y * g.y, xr.z * g.z, xr.w * g.w);
-              if (KIND == STAG_NOISE_EXTERNAL) {
-                if (p.dw_ext) {
-                  float* base = p.dw_ext + (int64_t)s * p.E * p.K;
-                  if (p.K == 1) {
-                    const float tot = group_sum(dw.x + dw.y + dw.z + dw.w, LPR);
-                    // several channel chunks accumulate into the same slot, from the same thread
-                    if (sl == 0 && (t0 + k < LPR) && (off + t0 + k < len)) {
-                      if (c0 == 0) base[ee[k]] = tot; else base[ee[k]] += tot;
+              // -------- per-channel weights, general path -----------------------------------------
+              float w[8], raw[8], pre[8];
+              if (MODE == 1) {
+                if (act[k]) {
+                  load8<VEC>(p.ext + ((int64_t)s * p.E + ee[k]) * p.K, c, p.K, w);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) w[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pre[i] = raw[i] = w[i];
+              } else {
+                raw_oct<KIND>((uint32_t)ee[k], oct, smp, p.key, raw);
+                if (PSH == 0) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) w[i] = transform<KIND>(raw[i], sa[k], sb[k]);
+                } else if (PSH == 1) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) w[i] = transform<KIND>(raw[i], P0[i], P1[i]);
+                } else {
+                  float a[8], b[8];
+                  if (act[k]) {
+                    load8<VEC>(p.p0 + (int64_t)ee[k] * p.K, c, p.K, a);
+                    if (KIND != STAG_NOISE_BERNOULLI) load8<VEC>(p.p1 + (int64_t)ee[k] * p.K, c, p.K, b);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+                  }
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) w[i] = transform<KIND>(raw[i], a[i], b[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pre[i] = w[i];
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = fmaxf(w[i], 0.f);
+              }
+              float g[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                g[i] = xv[k][i] * ssc[k];
+                acc[i] = fmaf(w[i], g[i], acc[i]);
+              }
+              if (!GRADS) {
+                if (p.in_norm && act[k]) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) wsum[i] += w[i];
+                }
+              } else {
+                float dw[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dw[i] = xr[i] * g[i];
+                if (MODE == 1) {
+                  if (p.dw_ext && act[k])
+                    store8<VEC, false>(p.dw_ext + ((int64_t)s * p.E + ee[k]) * p.K, c, p.K, dw);
+                } else if (PGRADS_C) {
+                  float e0[8], e1[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float e = (p.relu && !(pre[i] > 0.f)) ? 0.f : dw[i];
+                    e1[i] = e * raw[i];
+                    e0[i] = KIND == STAG_NOISE_NORMAL ? e : e - e1[i];
+                  }
+                  if (p.pshape <= STAG_PARAM_CHANNEL) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      d0[i] += e0[i];
+                      d1[i] += e1[i];
+                    }
+                  } else if (p.pshape == STAG_PARAM_EDGE) {
+                    const float t0s = group_sum(sum8(e0), LPR);
+                    const float t1s = group_sum(sum8(e1), LPR);
+                    if (sl == 0 && edge_ok) {
+                      p.dp0[ee[k]] += t0s;
+                      p.dp1[ee[k]] += t1s;
                     }
                   } else if (act[k]) {
-                    store4<ALIGNED>(base + (int64_t)ee[k] * p.K, c, p.K, dw);
+                    float* q0 = p.dp0 + (int64_t)ee[k] * p.K;
+                    float* q1 = p.dp1 + (int64_t)ee[k] * p.K;
+                    float o0[8], o1[8];
+                    load8<VEC>(q0, c, p.K, o0);
+                    load8<VEC>(q1, c, p.K, o1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      o0[i] += e0[i];
+                      o1[i] += e1[i];
+                    }
+                    store8<VEC, false>(q0, c, p.K, o0);
+                    store8<VEC, false>(q1, c, p.K, o1);
                   }
-                }
-              } else if (PARAM_GRADS) {
-                if (p.relu) {
-                  dw.x = pre.x > 0.f ? dw.x : 0.f;
-                  dw.y = pre.y > 0.f ? dw.y : 0.f;
-                  dw.z = pre.z > 0.f ? dw.z : 0.f;
-                  dw.w = pre.w > 0.f ? dw.w : 0.f;
-                }
-                float4 e0, e1;
-                if (KIND == STAG_NOISE_NORMAL) {
-                  e0 = dw;
-                  e1 = make_float4(dw.x * raw.x, dw.y * raw.y, dw.z * raw.z, dw.w * raw.w);
-                } else {
-                  e1 = make_float4(dw.x * raw.x, dw.y * raw.y, dw.z * raw.z, dw.w * raw.w);
-                  e0 = make_float4(dw.x - e1.x, dw.y - e1.y, dw.z - e1.z, dw.w - e1.w);
-                }
-                if (p.pshape <= STAG_PARAM_CHANNEL) {
-                  d0.x += e0.x; d0.y += e0.y; d0.z += e0.z; d0.w += e0.w;
-                  d1.x += e1.x; d1.y += e1.y; d1.z += e1.z; d1.w += e1.w;
-                } else if (p.pshape == STAG_PARAM_EDGE || p.K == 1) {
-                  const float t0s = group_sum(e0.x + e0.y + e0.z + e0.w, LPR);
-                  const float t1s = group_sum(e1.x + e1.y + e1.z + e1.w, LPR);
-                  if (sl == 0 && (t0 + k < LPR) && (off + t0 + k < len)) {
-                    p.dp0[ee[k]] += t0s;
-                    p.dp1[ee[k]] += t1s;
-                  }
-                } else if (act[k]) {
-                  float* q0 = p.dp0 + (int64_t)ee[k] * p.K;
-                  float* q1 = p.dp1 + (int64_t)ee[k] * p.K;
-                  float4 o0 = load4<ALIGNED>(q0, c, p.K), o1 = load4<ALIGNED>(q1, c, p.K);
-                  o0.x += e0.x; o0.y += e0.y; o0.z += e0.z; o0.w += e0.w;
-                  o1.x += e1.x; o1.y += e1.y; o1.z += e1.z; o1.w += e1.w;
-                  store4<ALIGNED>(q0, c, p.K, o0);
-                  store4<ALIGNED>(q1, c, p.K, o1);
                 }
               }
             }
@@ -328,66 +471,83 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_kernel(const AggParams p) {
         }
       }
 
-      // epilogue for this channel chunk
+      // ---- epilogue of this channel chunk --------------------------------------------------------
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wsum[i] = wsum_e;
+      }
       if (row >= 0 && qvalid) {
         if (part_slot >= 0) {
           if (p.out) {
-            const int64_t o = ((int64_t)s * p.num_hub_segs + part_slot) * nq4 + c;
-            *reinterpret_cast<float4*>(p.part_acc + o) = acc;
-            if (!GRADS && p.in_norm) *reinterpret_cast<float4*>(p.part_w + o) = wsum;
+            const int64_t o = ((int64_t)s * p.num_hub_segs + part_slot) * D8 + c;
+            store8<true, false>(p.part_acc + o, 0, 8, acc);
+            if (!GRADS && p.in_norm) store8<true, false>(p.part_w + o, 0, 8, wsum);
           }
         } else if (p.out) {
           if (!GRADS && p.in_norm) {
             const float indeg = (float)len;
-            float4 sc4;
-            sc4.x = wsum.x != 0.f ? indeg / wsum.x : 1.f;
-            sc4.y = wsum.y != 0.f ? indeg / wsum.y : 1.f;
-            sc4.z = wsum.z != 0.f ? indeg / wsum.z : 1.f;
-            sc4.w = wsum.w != 0.f ? indeg / wsum.w : 1.f;
-            acc.x *= sc4.x; acc.y *= sc4.y; acc.z *= sc4.z; acc.w *= sc4.w;
+            float sc8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              sc8[i] = wsum[i] != 0.f ? indeg / wsum[i] : 1.f;
+              acc[i] *= sc8[i];
+            }
             if (p.norm_scale_out) {
               float* ns = p.norm_scale_out + ((int64_t)s * p.N + row) * p.K;
-              if (p.K == 1) { if (c == 0) ns[0] = sc4.x; }
-              else store4<ALIGNED>(ns, c, p.K, sc4);
+              if (p.K == 1) {
+                if (c == 0) ns[0] = sc8[0];
+              } else {
+                store8<VEC, false>(ns, c, p.K, sc8);
+              }
             }
           }
-          acc.x *= rs; acc.y *= rs; acc.z *= rs; acc.w *= rs;
-          store4<ALIGNED>(p.out + (int64_t)s * p.out_ss + (int64_t)row * p.ldo, c, p.D, acc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] *= rs;
+          store8<VEC, true>(p.out + (int64_t)s * p.out_ss + (int64_t)row * p.ldo, c, p.D, acc);
         }
       }
-      if (PARAM_GRADS && p.pshape <= STAG_PARAM_CHANNEL) {
-        // fold the row groups of this warp, then add into the warp's shared slice
-        for (int o = LPR; o < 32; o <<= 1) {
-          d0.x += __shfl_xor_sync(0xffffffffu, d0.x, o);
-          d0.y += __shfl_xor_sync(0xffffffffu, d0.y, o);
-          d0.z += __shfl_xor_sync(0xffffffffu, d0.z, o);
-          d0.w += __shfl_xor_sync(0xffffffffu, d0.w, o);
-          d1.x += __shfl_xor_sync(0xffffffffu, d1.x, o);
-          d1.y += __shfl_xor_sync(0xffffffffu, d1.y, o);
-          d1.z += __shfl_xor_sync(0xffffffffu, d1.z, o);
-          d1.w += __shfl_xor_sync(0xffffffffu, d1.w, o);
-        }
-        if (sub == 0 && c < nq4) {
-          float4* a0 = reinterpret_cast<float4*>(my_sm + c);
-          float4* a1 = reinterpret_cast<float4*>(my_sm + nq4 + c);
-          float4 v0 = *a0, v1 = *a1;
-          v0.x += d0.x; v0.y += d0.y; v0.z += d0.z; v0.w += d0.w;
-          v1.x += d1.x; v1.y += d1.y; v1.z += d1.z; v1.w += d1.w;
-          *a0 = v0;
-          *a1 = v1;
+      if (GRADS && dense_pg) {
+        if (MODE == 0) {
+          // scalar parameter, per-edge noise: lane sl == 0 of each group holds this chunk's totals
+          float a = sl == 0 ? d0_e : 0.f, b = sl == 0 ? d1_e : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+          }
+          if (lane == 0) {
+            my_sm[0] += a;
+            my_sm[D8] += b;
+          }
+        } else {
+          // fold the row groups of this warp, then add into the warp's shared slice
+          for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              d0[i] += __shfl_xor_sync(0xffffffffu, d0[i], o);
+              d1[i] += __shfl_xor_sync(0xffffffffu, d1[i], o);
+            }
+          }
+          if (sub == 0 && c < D8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              my_sm[c + i] += d0[i];
+              my_sm[D8 + c + i] += d1[i];
+            }
+          }
         }
         __syncwarp();
       }
     }
   }
 
-  if (PARAM_GRADS && p.pshape <= STAG_PARAM_CHANNEL) {
+  if (GRADS && dense_pg) {
     __syncthreads();
-    float* dst = p.dp_partial + (size_t)blockIdx.x * 2 * nq4;
-    for (int i = threadIdx.x; i < 2 * nq4; i += AGG_THREADS) {
+    float* dst = p.dp_partial + (size_t)blockIdx.x * 2 * D8;
+    for (int i = threadIdx.x; i < 2 * D8; i += AGG_THREADS) {
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < AGG_WARPS; ++w) v += smem[(size_t)w * 2 * nq4 + i];
+      for (int w = 0; w < AGG_WARPS; ++w) v += smem[(size_t)w * 2 * D8 + i];
       dst[i] = v;
     }
   }
@@ -396,7 +556,7 @@ __global__ void __launch_bounds__(AGG_THREADS) agg_kernel(const AggParams p) {
 // Combine the partial sums of hub rows in segment order and finish the row.
 __global__ void hub_finalize_kernel(const AggParams p, int grads) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nq4 = p.nq * 4;
+  const int D8 = p.noct * 8;
   const int64_t total = (int64_t)p.S * p.num_hubs * p.D;
   if (idx >= total) return;
   const int c = (int)(idx % p.D);
@@ -406,7 +566,7 @@ __global__ void hub_finalize_kernel(const AggParams p, int grads) {
   const int s0 = p.hub_seg_ptr[h], s1 = p.hub_seg_ptr[h + 1];
   float acc = 0.f, wsum = 0.f;
   for (int seg = s0; seg < s1; ++seg) {
-    const int64_t o = ((int64_t)s * p.num_hub_segs + seg) * nq4 + c;
+    const int64_t o = ((int64_t)s * p.num_hub_segs + seg) * D8 + c;
     acc += p.part_acc[o];
     if (!grads && p.in_norm) wsum += p.part_w[o];
   }
@@ -422,7 +582,7 @@ __global__ void hub_finalize_kernel(const AggParams p, int grads) {
 }
 
 // Reduce per-CTA parameter-gradient partials in CTA order (deterministic).
-__global__ void param_finalize_kernel(const float* __restrict__ partial, int ncta, int nq4, int D, int scalar,
+__global__ void param_finalize_kernel(const float* __restrict__ partial, int ncta, int D8, int D, int scalar,
                                       float* __restrict__ dp0, float* __restrict__ dp1) {
   __shared__ float red[2][256];
   const int tid = threadIdx.x;
@@ -431,8 +591,8 @@ __global__ void param_finalize_kernel(const float* __restrict__ partial, int nct
     if (c >= D) return;
     float a = 0.f, b = 0.f;
     for (int k = 0; k < ncta; ++k) {
-      a += partial[(size_t)k * 2 * nq4 + c];
-      b += partial[(size_t)k * 2 * nq4 + nq4 + c];
+      a += partial[(size_t)k * 2 * D8 + c];
+      b += partial[(size_t)k * 2 * D8 + D8 + c];
     }
     dp0[c] = a;
     dp1[c] = b;
@@ -440,8 +600,8 @@ __global__ void param_finalize_kernel(const float* __restrict__ partial, int nct
     float a = 0.f, b = 0.f;
     for (int c = tid; c < D; c += blockDim.x) {
       for (int k = 0; k < ncta; ++k) {
-        a += partial[(size_t)k * 2 * nq4 + c];
-        b += partial[(size_t)k * 2 * nq4 + nq4 + c];
+        a += partial[(size_t)k * 2 * D8 + c];
+        b += partial[(size_t)k * 2 * D8 + D8 + c];
       }
     }
     red[0][tid] = a;
@@ -464,33 +624,32 @@ __global__ void param_finalize_kernel(const float* __restrict__ partial, int nct
 // noise materialisation (compat path + RNG tests): w[s,e,c]
 template <int KIND>
 __global__ void emit_kernel(const AggParams p, float* __restrict__ w_out, float* __restrict__ eps_out) {
-  const int nq = p.nq;
-  const int64_t total = (int64_t)p.S * p.E * nq;
+  const int noct = p.noct;
+  const int64_t total = (int64_t)p.S * p.E * noct;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % nq);
-    const int64_t e = (i / nq) % p.E;
-    const int s = (int)(i / ((int64_t)nq * p.E));
-    const int c = q * 4;
-    float4 P0 = f4zero(), P1 = f4zero();
-    if (p.pshape <= STAG_PARAM_CHANNEL) {
-      if (p.pshape == STAG_PARAM_SCALAR || p.K == 1) {
-        P0 = bcast4(p.p0[0]);
-        if (p.p1) P1 = bcast4(p.p1[0]);
-      } else {
-        P0 = load4<false>(p.p0, c, p.K);
-        if (p.p1) P1 = load4<false>(p.p1, c, p.K);
+    const int q = (int)(i % noct);
+    const int64_t e = (i / noct) % p.E;
+    const int s = (int)(i / ((int64_t)noct * p.E));
+    const int c = q * 8;
+    float raw[8];
+    raw_oct<KIND>((uint32_t)e, (uint32_t)q, (uint32_t)(p.sample_base + s), p.key, raw);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c + j < p.K) {
+        int64_t pi;
+        switch (p.pshape) {
+          case STAG_PARAM_SCALAR: pi = 0; break;
+          case STAG_PARAM_CHANNEL: pi = c + j; break;
+          case STAG_PARAM_EDGE: pi = e; break;
+          default: pi = e * p.K + c + j; break;
+        }
+        float w = transform<KIND>(raw[j], p.p0[pi], p.p1 ? p.p1[pi] : 0.f);
+        if (p.relu) w = fmaxf(w, 0.f);
+        const int64_t o = ((int64_t)s * p.E + e) * p.K + c + j;
+        w_out[o] = w;
+        if (eps_out) eps_out[o] = raw[j];
       }
-    }
-    float4 raw, pre;
-    const float4 w = noise_quad<KIND, false>(p, e, c, s, P0, P1, raw, pre);
-    const int64_t o = ((int64_t)s * p.E + e) * p.K;
-    if (p.K == 1) {
-      w_out[o] = w.x;
-      if (eps_out) eps_out[o] = raw.x;
-    } else {
-      store4<false>(w_out + o, c, p.K, w);
-      if (eps_out) store4<false>(eps_out + o, c, p.K, raw);
     }
   }
 }
@@ -508,9 +667,9 @@ __global__ void segment_reduce_kernel(const float* __restrict__ feat, int64_t ld
   out[(int64_t)b * ldo + c] = acc;
 }
 
-static int lpr_log2_for(int nq) {
+static int lpr_log2_for(int noct) {
   int l = 0;
-  while ((1 << l) < nq && l < 5) ++l;
+  while ((1 << l) < noct && l < 5) ++l;
   return l;
 }
 
@@ -520,14 +679,14 @@ struct WsLayout {
 
 static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
   WsLayout L;
-  const size_t nq4 = (size_t)((D + 3) / 4) * 4;
+  const size_t D8 = (size_t)((D + 7) / 8) * 8;
   size_t off = 0;
   L.part_acc = off;
-  off += align_up((size_t)S * g->num_hub_segs * nq4 * 4 + 16, 256);
+  off += align_up((size_t)S * g->num_hub_segs * D8 * 4 + 16, 256);
   L.part_w = off;
-  off += align_up((size_t)S * g->num_hub_segs * nq4 * 4 + 16, 256);
+  off += align_up((size_t)S * g->num_hub_segs * D8 * 4 + 16, 256);
   L.dp_partial = off;
-  off += align_up((size_t)grid_max * 2 * nq4 * 4 + 16, 256);
+  off += align_up((size_t)grid_max * 2 * D8 * 4 + 16, 256);
   L.total = off;
   return L;
 }
@@ -536,54 +695,71 @@ static int grid_cap() { return num_sms() * 8; }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-static int check_noise(const StagNoise* n, int D, const char* who) {
+static int check_noise(const StagNoise* n, int D, int64_t E, const char* who) {
   STAG_CHECK_ARG(n != nullptr, "%s: null noise spec", who);
   STAG_CHECK_ARG(n->kind >= STAG_NOISE_NONE && n->kind <= STAG_NOISE_BERNOULLI, "%s: bad noise kind %d", who, n->kind);
   if (n->kind == STAG_NOISE_NONE) return STAG_OK;
   STAG_CHECK_ARG(n->K == 1 || n->K == D, "%s: noise width K=%d must be 1 or D=%d", who, n->K, D);
   if (n->kind == STAG_NOISE_EXTERNAL) {
-    STAG_CHECK_ARG(n->external != nullptr, "%s: EXTERNAL noise needs a tensor", who);
+    STAG_CHECK_ARG(n->external != nullptr || E == 0, "%s: EXTERNAL noise needs a tensor", who);
     return STAG_OK;
   }
   STAG_CHECK_ARG(n->param_shape >= STAG_PARAM_SCALAR && n->param_shape <= STAG_PARAM_EDGE_CHANNEL,
                  "%s: bad param_shape %d", who, n->param_shape);
-  STAG_CHECK_ARG(n->p0 != nullptr, "%s: null parameter p0", who);
-  STAG_CHECK_ARG(n->kind == STAG_NOISE_BERNOULLI || n->p1 != nullptr, "%s: null parameter p1", who);
+  const bool per_edge = n->param_shape >= STAG_PARAM_EDGE;
+  STAG_CHECK_ARG(n->p0 != nullptr || (per_edge && E == 0), "%s: null parameter p0", who);
+  STAG_CHECK_ARG(n->kind == STAG_NOISE_BERNOULLI || n->p1 != nullptr || (per_edge && E == 0),
+                 "%s: null parameter p1", who);
   return STAG_OK;
 }
 
-
-template <int KIND, bool GRADS>
-static int launch_agg_kind(const AggParams& p, bool aligned, int grid, size_t smem, cudaStream_t stream) {
-  if (aligned) {
+template <int MODE, int KIND, int PSH, bool GRADS, bool FOLD = false>
+static int launch_vec(const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
+  if (vec) {
     if (smem > 48 * 1024)
-      STAG_CUDA(cudaFuncSetAttribute(agg_kernel<KIND, true, GRADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    agg_kernel<KIND, true, GRADS><<<grid, AGG_THREADS, smem, stream>>>(p);
+      STAG_CUDA(cudaFuncSetAttribute(agg_kernel<MODE, KIND, PSH, true, GRADS, FOLD>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    agg_kernel<MODE, KIND, PSH, true, GRADS, FOLD><<<grid, AGG_THREADS, smem, stream>>>(p);
   } else {
     if (smem > 48 * 1024)
-      STAG_CUDA(cudaFuncSetAttribute(agg_kernel<KIND, false, GRADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    agg_kernel<KIND, false, GRADS><<<grid, AGG_THREADS, smem, stream>>>(p);
+      STAG_CUDA(cudaFuncSetAttribute(agg_kernel<MODE, KIND, PSH, false, GRADS, FOLD>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    agg_kernel<MODE, KIND, PSH, false, GRADS, FOLD><<<grid, AGG_THREADS, smem, stream>>>(p);
   }
   STAG_LAUNCH_CHECK();
   return STAG_OK;
 }
 
-template <bool GRADS>
-static int launch_agg(int kind, const AggParams& p, bool aligned, int grid, size_t smem, cudaStream_t stream) {
-  switch (kind) {
-    case STAG_NOISE_NONE: return launch_agg_kind<STAG_NOISE_NONE, GRADS>(p, aligned, grid, smem, stream);
-    case STAG_NOISE_EXTERNAL: return launch_agg_kind<STAG_NOISE_EXTERNAL, GRADS>(p, aligned, grid, smem, stream);
-    case STAG_NOISE_NORMAL: return launch_agg_kind<STAG_NOISE_NORMAL, GRADS>(p, aligned, grid, smem, stream);
-    case STAG_NOISE_UNIFORM: return launch_agg_kind<STAG_NOISE_UNIFORM, GRADS>(p, aligned, grid, smem, stream);
-    case STAG_NOISE_BERNOULLI: return launch_agg_kind<STAG_NOISE_BERNOULLI, GRADS>(p, aligned, grid, smem, stream);
+template <int KIND, bool GRADS>
+static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
+  if (!GRADS && psh == 0 && !p.relu && !p.in_norm)
+    return launch_vec<2, KIND, 0, false, true>(p, vec, grid, smem, stream);
+  switch (psh) {
+    case 0: return launch_vec<2, KIND, 0, GRADS>(p, vec, grid, smem, stream);
+    case 1: return launch_vec<2, KIND, 1, GRADS>(p, vec, grid, smem, stream);
+    default: return launch_vec<2, KIND, 2, GRADS>(p, vec, grid, smem, stream);
   }
-  set_error("launch_agg: bad kind %d", kind);
+}
+
+template <bool GRADS>
+static int launch_agg(const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
+  if (p.kind == STAG_NOISE_NONE || p.K == 1) return launch_vec<0, 0, 0, GRADS>(p, vec, grid, smem, stream);
+  if (p.kind == STAG_NOISE_EXTERNAL) return launch_vec<1, 0, 0, GRADS>(p, vec, grid, smem, stream);
+  // generated per-channel noise: scalar / per-edge parameters travel with the edge record (PSH 0),
+  // per-channel parameters live in registers (1), per-edge-per-channel ones are read per edge (2)
+  const int psh = (p.pshape == STAG_PARAM_SCALAR || p.pshape == STAG_PARAM_EDGE) ? 0
+                  : (p.pshape == STAG_PARAM_CHANNEL ? 1 : 2);
+  switch (p.kind) {
+    case STAG_NOISE_NORMAL: return launch_psh<STAG_NOISE_NORMAL, GRADS>(psh, p, vec, grid, smem, stream);
+    case STAG_NOISE_UNIFORM: return launch_psh<STAG_NOISE_UNIFORM, GRADS>(psh, p, vec, grid, smem, stream);
+    case STAG_NOISE_BERNOULLI: return launch_psh<STAG_NOISE_BERNOULLI, GRADS>(psh, p, vec, grid, smem, stream);
+  }
+  set_error("launch_agg: bad kind %d", p.kind);
   return STAG_EINVAL;
 }
 
 static void fill_noise(AggParams& p, const StagNoise* n, int D) {
+  p.kind = n->kind;
   p.K = n->kind == STAG_NOISE_NONE ? D : n->K;
   p.pshape = n->param_shape;
   if (p.K == 1 && p.pshape == STAG_PARAM_CHANNEL) p.pshape = STAG_PARAM_SCALAR;
@@ -604,6 +780,7 @@ static void fill_graph(AggParams& p, const StagGraph* g) {
   p.eid = g->eid;
   p.hub_rows = g->hub_rows;
   p.hub_seg_ptr = g->hub_seg_ptr;
+  p.row_order = g->row_order;
   p.num_hubs = g->num_hubs;
   p.num_hub_segs = g->num_hub_segs;
   p.N = (int)g->num_rows;
@@ -620,10 +797,35 @@ static int check_graph(const StagGraph* g, const char* who) {
   return STAG_OK;
 }
 
+// Channel tiling: D, S -> octs, column blocks, lanes per row.  `gathered_rows` is the number of
+// rows of the gathered operand; blocks are only used when one [rows, D] operand does not fit the
+// part of L2 a gather can count on (kL2Operand), and never in gradient mode (per-edge outputs
+// are accumulated across channel chunks by one warp).
+constexpr size_t kL2Operand = 40u << 20;
+
+static void set_shape(AggParams& p, int D, int S, int64_t gathered_rows, bool shared_operand, bool grads) {
+  p.D = D;
+  p.S = S;
+  p.noct = (D + 7) / 8;
+  const int D8 = p.noct * 8;
+  int ncb = 1;
+  if (!grads) {
+    const size_t bytes = (size_t)gathered_rows * D * 4;
+    ncb = (int)((bytes + kL2Operand - 1) / kL2Operand);
+    if (ncb < 1) ncb = 1;
+  }
+  int cw = ((D8 + ncb - 1) / ncb + 31) / 32 * 32;  // whole 128-byte lines per gathered row
+  if (cw > D8) cw = D8;
+  p.cw = cw;
+  p.ncb = (D8 + cw - 1) / cw;
+  p.cb_major = shared_operand && S > 1;
+  p.lpr_log2 = lpr_log2_for(cw / 8);
+}
+
 static int agg_grid(const AggParams& p) {
   const int RPW = 32 >> p.lpr_log2;
   const int64_t per_sample = (int64_t)(p.num_hub_segs + RPW - 1) / RPW + (p.N + RPW - 1) / RPW;
-  const int64_t ctas = (per_sample * p.S + AGG_WARPS - 1) / AGG_WARPS;
+  const int64_t ctas = (per_sample * p.S * p.ncb + AGG_WARPS - 1) / AGG_WARPS;
   const int64_t cap = grid_cap();
   return (int)(ctas < 1 ? 1 : (ctas < cap ? ctas : cap));
 }
@@ -648,7 +850,7 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
   STAG_CHECK_ARG(out != nullptr, "stag_spmm_fwd: null output");
   STAG_CHECK_ARG(x != nullptr || g->num_edges == 0, "stag_spmm_fwd: null features");
   STAG_CHECK_ARG(ldx >= D && ldo >= D, "stag_spmm_fwd: row strides smaller than D");
-  rc = check_noise(noise, D, "stag_spmm_fwd");
+  rc = check_noise(noise, D, g->num_edges, "stag_spmm_fwd");
   if (rc) return rc;
   if (g->num_rows == 0) return STAG_OK;
   const WsLayout L = ws_layout(g, D, S, grid_cap());
@@ -662,20 +864,19 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
   p.x = x; p.ldx = ldx; p.x_ss = x_sample_stride;
   p.gscale = src_scale; p.rscale = dst_scale;
   p.out = out; p.ldo = ldo; p.out_ss = out_sample_stride;
-  p.D = D; p.S = S; p.nq = (D + 3) / 4;
-  p.lpr_log2 = lpr_log2_for(p.nq);
+  set_shape(p, D, S, g->num_cols, x_sample_stride == 0, false);
   p.norm_scale_out = norm_scale_out;
   if (g->num_hub_segs > 0) {
     p.part_acc = (float*)((char*)ws + L.part_acc);
     p.part_w = (float*)((char*)ws + L.part_w);
   }
-  bool aligned = (D % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (x_sample_stride % 4 == 0) &&
-                 (out_sample_stride % 4 == 0) && aligned16(x) && aligned16(out);
-  if (noise->kind == STAG_NOISE_EXTERNAL && noise->K != 1) aligned = aligned && aligned16(noise->external);
+  bool vec = (D % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (x_sample_stride % 4 == 0) &&
+             (out_sample_stride % 4 == 0) && aligned16(x) && aligned16(out);
+  if (noise->kind == STAG_NOISE_EXTERNAL && noise->K != 1) vec = vec && aligned16(noise->external);
   if (noise->kind >= STAG_NOISE_NORMAL && noise->param_shape != STAG_PARAM_SCALAR && noise->K != 1)
-    aligned = aligned && aligned16(noise->p0) && (noise->p1 == nullptr || aligned16(noise->p1));
-  if (norm_scale_out && noise->K != 1) aligned = aligned && aligned16(norm_scale_out);
-  rc = launch_agg<false>(noise->kind, p, aligned, agg_grid(p), 0, stream);
+    vec = vec && aligned16(noise->p0) && (noise->p1 == nullptr || aligned16(noise->p1));
+  if (norm_scale_out && noise->K != 1) vec = vec && aligned16(norm_scale_out);
+  rc = launch_agg<false>(p, vec, agg_grid(p), 0, stream);
   if (rc) return rc;
   if (g->num_hubs > 0) {
     const int64_t total = (int64_t)S * g->num_hubs * D;
@@ -697,7 +898,7 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   STAG_CHECK_ARG(dout != nullptr || g->num_edges == 0, "stag_spmm_bwd: null upstream gradient");
   STAG_CHECK_ARG(x != nullptr || g->num_edges == 0, "stag_spmm_bwd: null features");
   STAG_CHECK_ARG(ldx >= D && ldg >= D && (dx == nullptr || lddx >= D), "stag_spmm_bwd: row strides smaller than D");
-  rc = check_noise(noise, D, "stag_spmm_bwd");
+  rc = check_noise(noise, D, g->num_edges, "stag_spmm_bwd");
   if (rc) return rc;
   if (noise->in_norm) {
     set_error("stag_spmm_bwd: in_norm has no fused parameter-gradient path (use the emitted-noise path)");
@@ -728,26 +929,25 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   p.gscale = dst_scale; p.rscale = src_scale;
   p.out = dx; p.ldo = lddx; p.out_ss = dx_sample_stride;
   p.xrow = x; p.ldxr = ldx; p.xr_ss = x_sample_stride;
-  p.D = D; p.S = S; p.nq = (D + 3) / 4;
-  p.lpr_log2 = lpr_log2_for(p.nq);
+  set_shape(p, D, S, g->num_cols, false, true);
   p.dp0 = dparam0; p.dp1 = dparam1; p.dw_ext = dw_external;
   p.part_acc = (float*)((char*)ws + L.part_acc);
   p.part_w = (float*)((char*)ws + L.part_w);
   p.dp_partial = (float*)((char*)ws + L.dp_partial);
-  bool aligned = (D % 4 == 0) && (ldx % 4 == 0) && (ldg % 4 == 0) && (x_sample_stride % 4 == 0) &&
-                 (dout_sample_stride % 4 == 0) && aligned16(x) && aligned16(dout);
-  if (dx) aligned = aligned && (lddx % 4 == 0) && (dx_sample_stride % 4 == 0) && aligned16(dx);
+  bool vec = (D % 4 == 0) && (ldx % 4 == 0) && (ldg % 4 == 0) && (x_sample_stride % 4 == 0) &&
+             (dout_sample_stride % 4 == 0) && aligned16(x) && aligned16(dout);
+  if (dx) vec = vec && (lddx % 4 == 0) && (dx_sample_stride % 4 == 0) && aligned16(dx);
   if (noise->kind == STAG_NOISE_EXTERNAL && noise->K != 1)
-    aligned = aligned && aligned16(noise->external) && (dw_external == nullptr || aligned16(dw_external));
+    vec = vec && aligned16(noise->external) && (dw_external == nullptr || aligned16(dw_external));
   if (param_grads && noise->param_shape != STAG_PARAM_SCALAR && noise->K != 1)
-    aligned = aligned && aligned16(noise->p0) && aligned16(noise->p1) && aligned16(dparam0) && aligned16(dparam1);
+    vec = vec && aligned16(noise->p0) && aligned16(noise->p1) && aligned16(dparam0) && aligned16(dparam1);
   const int grid = agg_grid(p);
-  const size_t smem = (param_grads && !edge_params) ? (size_t)AGG_WARPS * 2 * p.nq * 4 * sizeof(float) : 0;
+  const size_t smem = (param_grads && !edge_params) ? (size_t)AGG_WARPS * 2 * p.noct * 8 * sizeof(float) : 0;
   if (smem > 200 * 1024) {
     set_error("stag_spmm_bwd: D=%d too wide for the shared-memory parameter-gradient staging", D);
     return STAG_EUNSUPPORTED;
   }
-  rc = launch_agg<true>(noise->kind, p, aligned, grid, smem, stream);
+  rc = launch_agg<true>(p, vec, grid, smem, stream);
   if (rc) return rc;
   if (g->num_hubs > 0 && dx) {
     const int64_t total = (int64_t)S * g->num_hubs * D;
@@ -757,7 +957,7 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   if (param_grads && !edge_params) {
     const int scalar = p.pshape == STAG_PARAM_SCALAR;
     const int blocks = scalar ? 1 : (D + 255) / 256;
-    param_finalize_kernel<<<blocks, 256, 0, stream>>>(p.dp_partial, grid, p.nq * 4, D, scalar, dparam0, dparam1);
+    param_finalize_kernel<<<blocks, 256, 0, stream>>>(p.dp_partial, grid, p.noct * 8, D, scalar, dparam0, dparam1);
     STAG_LAUNCH_CHECK();
   }
   return STAG_OK;
@@ -770,16 +970,17 @@ extern "C" int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_
   STAG_CHECK_ARG(noise->kind >= STAG_NOISE_NORMAL && noise->kind <= STAG_NOISE_BERNOULLI,
                  "stag_noise_emit: kind %d is not a generated distribution", noise->kind);
   STAG_CHECK_ARG(noise->K > 0 && S > 0 && num_edges >= 0 && num_edges < (1ll << 31), "stag_noise_emit: bad sizes");
-  int rc = check_noise(noise, noise->K, "stag_noise_emit");
+  int rc = check_noise(noise, noise->K, num_edges, "stag_noise_emit");
   if (rc) return rc;
   if (num_edges == 0) return STAG_OK;
   AggParams p = {};
   fill_noise(p, noise, noise->K);
+  p.ncb = 1;
   p.E = num_edges;
   p.S = S;
   p.D = noise->K;
-  p.nq = (noise->K + 3) / 4;
-  const int64_t total = (int64_t)S * num_edges * p.nq;
+  p.noct = (noise->K + 7) / 8;
+  const int64_t total = (int64_t)S * num_edges * p.noct;
   const int64_t want = (total + 255) / 256;
   const int grid = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
   switch (noise->kind) {

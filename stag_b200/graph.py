@@ -120,6 +120,7 @@ def build_csx(src, dst, num_nodes, by_dst):
         eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         hub_rows = torch.empty(E // thr + 1, dtype=torch.int32, device=dev)
         hub_seg_ptr = torch.empty(E // thr + 2, dtype=torch.int32, device=dev)
+        row_order = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
         ws_bytes = lib.stag_csx_workspace_bytes(E, N)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         counts = (ctypes.c_int32 * 2)()
@@ -127,14 +128,15 @@ def build_csx(src, dst, num_nodes, by_dst):
         _lib.check(lib.stag_csx_build(
             src.data_ptr(), dst.data_ptr(), E, N, 1 if by_dst else 0,
             indptr.data_ptr(), indices.data_ptr(), eid.data_ptr(),
-            hub_rows.data_ptr(), hub_seg_ptr.data_ptr(), counts,
+            hub_rows.data_ptr(), hub_seg_ptr.data_ptr(), row_order.data_ptr(), counts,
             ws.data_ptr(), ws_bytes, stream))
     g = _lib.StagGraph()
     g.num_rows, g.num_cols, g.num_edges = N, N, E
     g.indptr, g.indices, g.eid = indptr.data_ptr(), indices.data_ptr(), eid.data_ptr()
     g.num_hubs, g.num_hub_segs = int(counts[0]), int(counts[1])
     g.hub_rows, g.hub_seg_ptr = hub_rows.data_ptr(), hub_seg_ptr.data_ptr()
-    keep = {"indptr": indptr, "indices": indices[:E], "eid": eid[:E],
+    g.row_order = row_order.data_ptr() if N > 0 else None
+    keep = {"indptr": indptr, "indices": indices[:E], "eid": eid[:E], "row_order": row_order[:N],
             "hub_rows": hub_rows[:g.num_hubs], "hub_seg_ptr": hub_seg_ptr[:g.num_hubs + 1]}
     return g, keep
 

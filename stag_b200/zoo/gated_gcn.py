@@ -24,7 +24,11 @@ class GatedGCN(nn.Module):
         self.B = nn.Linear(input_dim, output_dim, bias=True)
         self.bn_node_h = nn.BatchNorm1d(output_dim)
 
-    def forward(self, g, h, edge_weight=None):
+    def forward(self, g=None, h=None, edge_weight=None, graph=None, feat=None):
+        # the reference names the arguments (g, h) (stag/zoo/gated_gcn.py:26) while StagLayer calls
+        # base_layer.forward(graph=, feat=, edge_weight=) (stag/layers.py:109-113): accept both
+        g = graph if g is None else g
+        h = feat if h is None else h
         if isinstance(edge_weight, ops.NoiseSpec) and edge_weight.batched:
             raise NotImplementedError("GatedGCN: BatchNorm makes sample batching per-sample; "
                                       "StagModel(batch_samples=False)")

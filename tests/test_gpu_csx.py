@@ -28,6 +28,10 @@ def check(src, dst, n, lib):
         assert g.num_hubs == len(rows) and g.num_hub_segs == int(segp[-1])
         assert np.array_equal(t["hub_rows"], rows)
         assert np.array_equal(t["hub_seg_ptr"], segp)
+        # row_order: a permutation of the rows by decreasing (clamped) degree, ties by decreasing id
+        deg = np.minimum(np.diff(indptr.astype(np.int64)), lib.stag_hub_threshold() + 1)
+        want = np.lexsort((np.arange(n), deg))[::-1]
+        assert np.array_equal(t["row_order"], want.astype(np.int32))
 
 
 @pytest.mark.parametrize("n,e", [(1, 0), (1, 7), (5, 0), (3, 9), (50, 300), (257, 4096), (1000, 4097),
@@ -77,5 +81,5 @@ def test_csx_rejects_bad_arguments(lib):
     from stag_b200 import _lib
     import ctypes
     counts = (ctypes.c_int32 * 2)()
-    rc = lib.stag_csx_build(0, 0, -1, 4, 1, 0, 0, 0, 0, 0, counts, 0, 0, 0)
+    rc = lib.stag_csx_build(0, 0, -1, 4, 1, 0, 0, 0, 0, 0, 0, counts, 0, 0, 0)
     assert rc == _lib.STAG_EINVAL and b"negative" in lib.stag_last_error()

@@ -50,7 +50,9 @@ def test_forward_gat_and_others():
     assert stag.layers.StagLayer(stag.zoo.GAT(16, 8, num_heads=4, last=True)).cuda()(g, h).shape == (30, 8)
     assert stag.layers.StagLayer(stag.zoo.GraphSAGE(16, 8)).cuda()(g, h).shape == (30, 8)
     assert stag.layers.StagLayer(stag.zoo.GIN(16, 8)).cuda()(g, h).shape == (30, 8)
-    assert stag.layers.StagLayer(stag.zoo.GatedGCN(16, 8)).cuda()(g, h).shape == (30, 8)
+    # the reference's GatedGCN adds A(h) [N,out] to the aggregate of raw h [N,in] (stag/zoo/gated_gcn.py:30-43):
+    # with edge weights it only works for input_dim == output_dim
+    assert stag.layers.StagLayer(stag.zoo.GatedGCN(16, 16)).cuda()(g, h).shape == (30, 16)
 
 
 def test_fused_layer_equals_tensor_path_on_its_own_sample():

@@ -187,5 +187,12 @@ def test_fused_parameter_gradients(kind, pshape, D, K):
     rel = lambda u, v: float((u.cpu() - v).abs().max() / v.abs().max().clamp(min=1e-30))  # noqa: E731
     assert rel(out, oo) < 1e-5
     assert rel(xc.grad, xo.grad) < 1e-5
-    assert rel(pa.grad, ao.grad) < 2e-5, rel(pa.grad, ao.grad)
-    assert rel(pb.grad, bo.grad) < 2e-5, rel(pb.grad, bo.grad)
+    # scalar / per-channel gradients are sums of ~E*D (E) signed terms of magnitude ~1: allow the fp32
+    # random-walk rounding of such a sum on top of the 1e-5 relative bound
+    n_terms = {"scalar": e * D, "channel": e, "edge": D if K > 1 else 1, "edge_channel": 1}[pshape]
+    slack = 1e-6 * np.sqrt(n_terms)
+
+    def ok(u, v):
+        return float((u.cpu() - v).abs().max()) <= 2e-5 * float(v.abs().max()) + slack
+    assert ok(pa.grad, ao.grad), (pa.grad, ao.grad)
+    assert ok(pb.grad, bo.grad), (pb.grad, bo.grad)
