@@ -87,6 +87,13 @@ typedef struct StagGraph {
   /* processing order of the rows (decreasing stored-edge count) so that rows sharing a warp have
    * equal trip counts; NULL = natural order.  Results do not depend on it. */
   const int32_t* row_order;    /* [num_rows] or NULL                              */
+  /* stream items: consecutive row ranges {row0, row1, e0, e1} holding about 64 stored edges each
+   * (e1 = -1: placeholder of a hub row), by decreasing edge count: the unit of work of the
+   * streaming kernels */
+  const int32_t* items;        /* [num_items][4] or NULL                          */
+  int64_t num_items;
+  const int32_t* erow;         /* [E] row of every stored edge (the sorted keys) or NULL */
+  const int32_t* eidf;         /* [E] eid with bit 31 set on the last stored edge of a row, or NULL */
 } StagGraph;
 
 /* Noise specification.  Parameter pointers are DEVICE pointers (they are nn.Parameters /
@@ -120,13 +127,17 @@ STAG_API int stag_hub_segment(void);
  *   hub_rows     capacity  E / stag_hub_threshold() + 1
  *   hub_seg_ptr  capacity  E / stag_hub_threshold() + 2
  *   row_order    [N] rows by decreasing degree (optional, may be NULL)
- *   counts_host  [2] host ints: {num_hubs, num_hub_segs}  (the call synchronises `stream`)
+ *   items        [stag_csx_items_capacity(E, N)][4] stream items (optional, may be NULL)
+ *   erow         [E] row of every stored edge (optional, may be NULL)
+ *   eidf         [E] eid | (last edge of its row) << 31 (optional, may be NULL)
+ *   counts_host  [3] host ints: {num_hubs, num_hub_segs, num_items}  (the call synchronises `stream`)
  */
 STAG_API size_t stag_csx_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+STAG_API int64_t stag_csx_items_capacity(int64_t num_edges, int64_t num_nodes);
 STAG_API int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t num_edges, int64_t num_nodes,
                    int by_dst, int32_t* indptr, int32_t* indices, int32_t* eid,
-                   int32_t* hub_rows, int32_t* hub_seg_ptr, int32_t* row_order, int32_t* counts_host,
-                   void* ws, size_t ws_bytes, void* stream);
+                   int32_t* hub_rows, int32_t* hub_seg_ptr, int32_t* row_order, int32_t* items,
+                   int32_t* erow, int32_t* eidf, int32_t* counts_host, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- fused stochastic aggregation ------------------------------------------------------
  * Forward (CSC graph), replaces rsample_noise + relu + _in_norm + update_all(u_mul_e, sum):

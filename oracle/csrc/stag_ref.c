@@ -118,14 +118,18 @@ API void ref_noise(int kind, int64_t E, int K, int sample, uint64_t seed, uint64
                    const float* p1, int pshape, int relu, float* w, float* raw) {
   if (K == 1 && pshape == P_CHANNEL) pshape = P_SCALAR;
   if (K == 1 && pshape == P_EDGE_CHANNEL) pshape = P_EDGE;
-  const int nq = (K + 7) / 8;
+  /* block q serves channels c0+{0..3} and c0+32+{0..3}, c0 = 64*(q/8) + 4*(q%8) */
+  const int rem = K % 64;
+  const int nq = 8 * (K / 64) + ((rem + 3) / 4 < 8 ? (rem + 3) / 4 : 8);
 #pragma omp parallel for schedule(static)
   for (int64_t e = 0; e < E; ++e) {
     for (int q = 0; q < nq; ++q) {
       float v[8];
       raw8(kind, (uint32_t)e, (uint32_t)q, (uint32_t)sample, seed, offset, v);
-      for (int i = 0; i < 8 && q * 8 + i < K; ++i) {
-        const int c = q * 8 + i;
+      const int c0 = 64 * (q / 8) + 4 * (q % 8);
+      for (int i = 0; i < 8; ++i) {
+        const int c = i < 4 ? c0 + i : c0 + 28 + i;
+        if (c >= K) continue;
         const float a = param_at(p0, pshape, e, c, K);
         const float b = p1 ? param_at(p1, pshape, e, c, K) : 0.0f;
         float x;

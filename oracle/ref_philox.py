@@ -11,15 +11,16 @@ Generator: Philox4x32 with ROUNDS = 7 rounds (Salmon et al., SC'11; Random123 co
 The round function is pinned against the Random123 known-answer vectors at 10 rounds
 (tests/test_oracle_cpu.py); 7 is the smallest Crush-resistant round count (ibid., table 2).
 
-Counter / key layout (one 128-bit block = the 8 channels 8q..8q+7, "oct" q, of one edge):
-    ctr = (eid, q, sample, offset_lo)      key = (seed_lo, seed_hi ^ offset_hi)
-Each output word r_i (i = 0..3) gives the variates of channels 8q+2i (from its low 16 bits
-h_lo) and 8q+2i+1 (from its high 16 bits h_hi):
+Counter / key layout (one 128-bit block b = 8 channels of one edge):
+    ctr = (eid, b, sample, offset_lo)      key = (seed_lo, seed_hi ^ offset_hi)
+    channels of block b: c(b)+{0..3} and c(b)+32+{0..3}, c(b) = 64*(b//8) + 4*(b%8)
+Each output word r_i (i = 0..3) gives slot 2i (from its low 16 bits h_lo) and slot 2i+1 (from its
+high 16 bits h_hi); slot j < 4 is channel c(b)+j, slot j >= 4 is channel c(b)+32+(j-4):
     uniform  : u = h / 65536                                          in [0, 1)
     normal   : u1 = (h_lo + 1/2) / 65536,  rad = sqrt(float32(-2 ln 2) * log2(u1))
                ang = fma(float32(2^23 + h_hi), float32(2 pi / 65536), float32(-2 pi (128 - 2^-17)))
                    ~ 2 pi (h_hi + 1/2) / 65536  (the fp32 fma is part of the definition)
-               z(8q+2i) = rad * cos(ang),  z(8q+2i+1) = rad * sin(ang)
+               z(slot 2i) = rad * cos(ang),  z(slot 2i+1) = rad * sin(ang)
     bernoulli: 1 if u < p else 0
 A per-edge noise (K == 1) uses q = 0 and the first variate only.
 """
@@ -68,18 +69,40 @@ def raw_block(eid, q, sample, seed, offset):
     return philox4x32(eid, q, sample, np.uint32(offset & 0xFFFFFFFF), k0, k1)
 
 
+def n_blocks(K):
+    rem = K % 64
+    return 8 * (K // 64) + min(8, (rem + 3) // 4)
+
+
+def block_channels(nblk):
+    """[nblk, 8] channel served by each slot of each block."""
+    b = np.arange(nblk)
+    c = 64 * (b // 8) + 4 * (b % 8)
+    return np.concatenate([c[:, None] + np.arange(4), c[:, None] + 32 + np.arange(4)], axis=1)
+
+
+def _to_channels(slots, K):
+    """[E, nblk, 8] per-slot values -> [E, K] per-channel values."""
+    E, nblk, _ = slots.shape
+    ch = block_channels(nblk)
+    out = np.zeros((E, max(int(ch.max()) + 1, K)), dtype=slots.dtype)
+    out[:, ch.reshape(-1)] = slots.reshape(E, -1)
+    return out[:, :K]
+
+
 def halves(num_edges, K, sample, seed, offset):
-    """uint32 [E, noct*8] -- the 16-bit integer h used for channel c of edge e (ORIGINAL edge order)."""
-    noct = (K + 7) // 8
+    """uint32 [E, nblk, 8] -- the 16-bit integer h of every slot of every block (ORIGINAL edge order)."""
+    nblk = n_blocks(K)
     eid = np.arange(num_edges, dtype=np.uint32)[:, None]
-    q = np.arange(noct, dtype=np.uint32)[None, :]
-    r = np.stack(raw_block(eid, q, np.uint32(sample), seed, offset), axis=-1)      # [E, noct, 4]
-    h = np.stack([r & np.uint32(0xFFFF), r >> np.uint32(16)], axis=-1)               # [E, noct, 4, 2]
-    return h.reshape(num_edges, noct * 8)
+    q = np.arange(nblk, dtype=np.uint32)[None, :]
+    r = np.stack(raw_block(eid, q, np.uint32(sample), seed, offset), axis=-1)      # [E, nblk, 4]
+    h = np.stack([r & np.uint32(0xFFFF), r >> np.uint32(16)], axis=-1)               # [E, nblk, 4, 2]
+    return h.reshape(num_edges, nblk, 8)
 
 
 def uniform(num_edges, K, sample, seed, offset):
-    return (halves(num_edges, K, sample, seed, offset)[:, :K].astype(np.float32) * np.float32(2.0 ** -16))
+    h = halves(num_edges, K, sample, seed, offset).astype(np.float32) * np.float32(2.0 ** -16)
+    return _to_channels(h, K)
 
 
 K_ANG = np.float64(np.float32(2.0 * np.pi / 65536.0))
@@ -88,13 +111,13 @@ M2LN2 = np.float64(np.float32(-2.0 * np.log(2.0)))
 
 
 def std_normal(num_edges, K, sample, seed, offset):
-    noct = (K + 7) // 8
-    h = halves(num_edges, K, sample, seed, offset).reshape(num_edges, noct * 4, 2).astype(np.float64)
+    nblk = n_blocks(K)
+    h = halves(num_edges, K, sample, seed, offset).reshape(num_edges, nblk * 4, 2).astype(np.float64)
     u1 = (h[..., 0] + 0.5) * 2.0 ** -16
     rad = np.sqrt(M2LN2 * np.log2(u1))
     ang = np.float32((8388608.0 + h[..., 1]) * K_ANG + C_ANG).astype(np.float64)   # exact fp32 fma
-    z = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=-1).reshape(num_edges, noct * 8)[:, :K]
-    return z.astype(np.float32)
+    z = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=-1).reshape(num_edges, nblk, 8)
+    return _to_channels(z.astype(np.float32), K)
 
 
 def noise(kind, num_edges, K, sample, seed, offset, p0=None, p1=None, relu=False):

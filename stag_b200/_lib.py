@@ -36,6 +36,7 @@ class StagGraph(ctypes.Structure):
         ("indptr", ctypes.c_void_p), ("indices", ctypes.c_void_p), ("eid", ctypes.c_void_p),
         ("num_hubs", ctypes.c_int32), ("num_hub_segs", ctypes.c_int32),
         ("hub_rows", ctypes.c_void_p), ("hub_seg_ptr", ctypes.c_void_p), ("row_order", ctypes.c_void_p),
+        ("items", ctypes.c_void_p), ("num_items", ctypes.c_int64), ("erow", ctypes.c_void_p), ("eidf", ctypes.c_void_p),
     ]
 
 
@@ -57,7 +58,8 @@ SIGNATURES = {
     "stag_hub_threshold": (_I, []),
     "stag_hub_segment": (_I, []),
     "stag_csx_workspace_bytes": (_SZ, [_I64, _I64]),
-    "stag_csx_build": (_I, [_V, _V, _I64, _I64, _I, _V, _V, _V, _V, _V, _V, c_i32p, _V, _SZ, _V]),
+    "stag_csx_items_capacity": (_I64, [_I64, _I64]),
+    "stag_csx_build": (_I, [_V, _V, _I64, _I64, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V, c_i32p, _V, _SZ, _V]),
     "stag_spmm_workspace_bytes": (_SZ, [_GP, _I32, _I32]),
     "stag_spmm_fwd": (_I, [_GP, _V, _I64, _I64, _I32, _I32, _NP, _V, _V, _V, _I64, _I64, _V, _V, _SZ, _V]),
     "stag_spmm_bwd": (_I, [_GP, _V, _I64, _I64, _V, _I64, _I64, _I32, _I32, _NP, _V, _V, _V, _I64, _I64,

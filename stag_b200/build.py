@@ -35,17 +35,18 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), lib_path=None):
     """Compile every .cu under csrc/ for sm_100a and link libstag_b200.so."""
+    lib_path = lib_path or LIB_PATH
     if not force and not _stale():
-        return LIB_PATH
+        return lib_path
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = _nvcc()
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -55,11 +56,11 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

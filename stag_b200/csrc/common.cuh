@@ -40,6 +40,8 @@ void set_error(const char* fmt, ...);
 
 constexpr int kHubThreshold = 128;  // rows with more stored edges than this are split
 constexpr int kHubSegment = 128;    // edges per hub segment
+constexpr int kRangeEdges = 64;     // row ranges (stream items) start a new item every this many stored edges
+constexpr int kRangeRows = 256;     // ... and at least every this many rows
 
 int num_sms();  // SM count of the current device (cached per device)
 

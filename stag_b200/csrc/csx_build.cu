@@ -137,14 +137,37 @@ __global__ void k_indptr_from_sorted(const uint32_t* __restrict__ keys, int64_t 
   for (int64_t v = prev + 1; v <= cur; ++v) indptr[v] = (int32_t)i;
 }
 
-__global__ void k_gather_other(const uint32_t* __restrict__ eid_sorted, const int64_t* __restrict__ other64,
-                               int64_t E, int32_t* __restrict__ indices, int32_t* __restrict__ eid) {
+__global__ void k_gather_other(const uint32_t* __restrict__ eid_sorted, const uint32_t* __restrict__ key_sorted,
+                               const int64_t* __restrict__ other64, int64_t E, int32_t* __restrict__ indices,
+                               int32_t* __restrict__ eid, int32_t* __restrict__ erow, int32_t* __restrict__ eidf) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < E) {
     const uint32_t e = eid_sorted[i];
     eid[i] = (int32_t)e;
     indices[i] = (int32_t)other64[e];
+    if (erow) erow[i] = (int32_t)key_sorted[i];
+    if (eidf) {
+      const bool last = i + 1 == E || key_sorted[i + 1] != key_sorted[i];
+      eidf[i] = (int32_t)(e | (last ? 0x80000000u : 0u));
+    }
   }
+}
+
+// stream items by decreasing edge count, so that the items sharing a warp have equal trip counts
+__global__ void k_item_keys(const int32_t* __restrict__ items, int64_t n, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    const int e1 = items[4 * k + 3];
+    keys[k] = e1 < 0 ? 0u : (uint32_t)min(e1 - items[4 * k + 2], 255);
+    vals[k] = (uint32_t)k;
+  }
+}
+
+__global__ void k_item_permute(const int4* __restrict__ src, const uint32_t* __restrict__ order, int64_t n,
+                               int4* __restrict__ dst) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[order[n - 1 - k]];
 }
 
 // hub schedule ---------------------------------------------------------------------------
@@ -191,8 +214,49 @@ __global__ void k_reverse_order(const uint32_t* __restrict__ sorted_rows, int64_
   if (i < N) row_order[i] = (int32_t)sorted_rows[N - 1 - i];
 }
 
+// ---- stream items: consecutive row ranges holding about kRangeEdges stored edges ---------------
+// A row starts a new item when it is the first row whose edges begin in a new block of kRangeEdges
+// positions, every kRangeRows rows, and around hub rows (a hub row is an item of its own that the
+// streaming kernel skips: its edges are processed as hub segments).  item = {row0, row1, e0, e1};
+// e1 = -1 marks a hub placeholder.
+__device__ __forceinline__ bool range_starts_at(const int32_t* __restrict__ indptr, int64_t v) {
+  if (v == 0 || (v % kRangeRows) == 0) return true;
+  const int b = indptr[v], a = indptr[v - 1], c = indptr[v + 1];
+  return (c - b > kHubThreshold) || (b - a > kHubThreshold) || (b / kRangeEdges != a / kRangeEdges);
+}
+
+__global__ void k_range_flags(const int32_t* __restrict__ indptr, int64_t N, uint32_t* __restrict__ flags) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N) flags[v] = range_starts_at(indptr, v) ? 1u : 0u;
+}
+
+__global__ void k_range_scatter(const int32_t* __restrict__ indptr, int64_t N, const uint32_t* __restrict__ pos,
+                                int32_t* __restrict__ items) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N && range_starts_at(indptr, v)) {
+    items[4 * (int64_t)pos[v] + 0] = (int32_t)v;
+    items[4 * (int64_t)pos[v] + 2] = indptr[v];
+  }
+}
+
+__global__ void k_range_close(const int32_t* __restrict__ indptr, int64_t N, const uint32_t* __restrict__ total,
+                              int32_t* __restrict__ items) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = total[0];
+  if (k >= n) return;
+  const int row0 = items[4 * k];
+  const int row1 = k + 1 < n ? items[4 * (k + 1)] : (int)N;
+  items[4 * k + 1] = row1;
+  const bool hub = indptr[row0 + 1] - indptr[row0] > kHubThreshold;
+  items[4 * k + 3] = hub ? -1 : indptr[row1];
+}
+
+}  // namespace stag
+extern "C" int64_t stag_csx_items_capacity(int64_t num_edges, int64_t num_nodes);
+namespace stag {
+
 struct CsxWorkspace {
-  uint32_t *keys_a, *vals_a, *keys_b, *vals_b, *hist, *flags_a, *flags_b, *totals;
+  uint32_t *keys_a, *vals_a, *keys_b, *vals_b, *hist, *flags_a, *flags_b, *totals, *items_tmp;
   int nblocks;
 };
 
@@ -216,6 +280,7 @@ static size_t carve(int64_t E, int64_t N, char* base, CsxWorkspace* w) {
   tmp.flags_a = take((size_t)(N + 1) * 4);
   tmp.flags_b = take((size_t)(N + 1) * 4);
   tmp.totals = take(256);
+  tmp.items_tmp = take((size_t)stag_csx_items_capacity(E, N) * 16);
   if (w) *w = tmp;
   return off;
 }
@@ -224,14 +289,20 @@ static size_t carve(int64_t E, int64_t N, char* base, CsxWorkspace* w) {
 
 using namespace stag;
 
+extern "C" int64_t stag_csx_items_capacity(int64_t num_edges, int64_t num_nodes) {
+  // one item per started block of kRangeEdges edge positions and of kRangeRows rows, plus up to three
+  // around every hub row
+  return num_edges / kRangeEdges + num_nodes / kRangeRows + 3 * (num_edges / (kHubThreshold + 1)) + 4;
+}
+
 extern "C" size_t stag_csx_workspace_bytes(int64_t num_edges, int64_t num_nodes) {
   return carve(num_edges, num_nodes, nullptr, nullptr);
 }
 
 extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E, int64_t N, int by_dst,
                               int32_t* indptr, int32_t* indices, int32_t* eid, int32_t* hub_rows,
-                              int32_t* hub_seg_ptr, int32_t* row_order, int32_t* counts_host, void* ws,
-                              size_t ws_bytes, void* stream_) {
+                              int32_t* hub_seg_ptr, int32_t* row_order, int32_t* items, int32_t* erow, int32_t* eidf, int32_t* counts_host,
+                              void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   STAG_CHECK_ARG(E >= 0 && N >= 0, "stag_csx_build: negative sizes");
   STAG_CHECK_ARG(E < (1ll << 31) && N < (1ll << 31) - 1, "stag_csx_build: E and N must be < 2^31");
@@ -273,7 +344,7 @@ extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E,
     k_indptr_from_sorted<<<(unsigned)((E + 1 + tb - 1) / tb), tb, 0, stream>>>(kin, E, N, indptr);
     STAG_LAUNCH_CHECK();
     if (E > 0) {
-      k_gather_other<<<(unsigned)((E + tb - 1) / tb), tb, 0, stream>>>(vin, other64, E, indices, eid);
+      k_gather_other<<<(unsigned)((E + tb - 1) / tb), tb, 0, stream>>>(vin, kin, other64, E, indices, eid, erow, eidf);
       STAG_LAUNCH_CHECK();
     }
   }
@@ -294,7 +365,7 @@ extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E,
     STAG_LAUNCH_CHECK();
   }
   // hub schedule
-  int32_t counts[2] = {0, 0};
+  int32_t counts[3] = {0, 0, 0};
   if (N > 0 && E > 0) {
     const int tb = 256;
     const unsigned gb = (unsigned)((N + tb - 1) / tb);
@@ -310,8 +381,40 @@ extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E,
   } else {
     STAG_CUDA(cudaMemsetAsync(hub_seg_ptr, 0, sizeof(int32_t), stream));
   }
+  // stream items
+  if (items && N > 0) {
+    const int tb = 256;
+    const unsigned gb = (unsigned)((N + tb - 1) / tb);
+    k_range_flags<<<gb, tb, 0, stream>>>(indptr, N, w.flags_a);
+    STAG_LAUNCH_CHECK();
+    k_exclusive_scan<<<1, 1024, 0, stream>>>(w.flags_a, N, w.totals + 2);
+    STAG_LAUNCH_CHECK();
+    k_range_scatter<<<gb, tb, 0, stream>>>(indptr, N, w.flags_a, items);
+    STAG_LAUNCH_CHECK();
+    k_range_close<<<gb, tb, 0, stream>>>(indptr, N, w.totals + 2, items);  // #items <= N
+    STAG_LAUNCH_CHECK();
+    STAG_CUDA(cudaMemcpyAsync(counts + 2, w.totals + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    STAG_CUDA(cudaStreamSynchronize(stream));
+    const int64_t n = counts[2];
+    if (n > 1) {  // order by decreasing edge count (one stable 8-bit radix pass), ties by decreasing row
+      const unsigned ib = (unsigned)((n + tb - 1) / tb);
+      const int nb = (int)((n + RS_TILE - 1) / RS_TILE);
+      k_item_keys<<<ib, tb, 0, stream>>>(items, n, w.keys_a, w.vals_a);
+      STAG_LAUNCH_CHECK();
+      k_radix_hist<<<nb, RS_THREADS, 0, stream>>>(w.keys_a, n, 0, w.hist, nb);
+      STAG_LAUNCH_CHECK();
+      k_exclusive_scan<<<1, 1024, 0, stream>>>(w.hist, (int64_t)RS_RADIX * nb, nullptr);
+      STAG_LAUNCH_CHECK();
+      k_radix_scatter<<<nb, RS_THREADS, 0, stream>>>(w.keys_a, w.vals_a, w.keys_b, w.vals_b, n, 0, w.hist, nb);
+      STAG_LAUNCH_CHECK();
+      STAG_CUDA(cudaMemcpyAsync(w.items_tmp, items, (size_t)n * 16, cudaMemcpyDeviceToDevice, stream));
+      k_item_permute<<<ib, tb, 0, stream>>>((const int4*)w.items_tmp, w.vals_b, n, (int4*)items);
+      STAG_LAUNCH_CHECK();
+    }
+  }
   STAG_CUDA(cudaStreamSynchronize(stream));
   counts_host[0] = counts[0];
   counts_host[1] = counts[1];
+  counts_host[2] = counts[2];
   return STAG_OK;
 }

@@ -49,7 +49,7 @@ extern "C" int stag_aggregate_host(int device, const int64_t* src, const int64_t
   int rc = STAG_OK;
   {
     DevBuf d_src, d_dst, d_x, d_out, d_dout, d_dxs, d_dx, d_p0, d_p1, d_ws, d_sw;
-    DevBuf csc[6], csr[6], d_ss, d_ds;
+    DevBuf csc[9], csr[9], d_ss, d_ds;
     const size_t nd = (size_t)N * D * 4;
     const size_t hubcap = (size_t)(E / kHubThreshold + 2) * 4;
 #define TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("stag_aggregate_host: %s -> %s", #call, cudaGetErrorString(e__)); rc = STAG_ECUDA; goto done; } } while (0)
@@ -66,16 +66,18 @@ extern "C" int stag_aggregate_host(int device, const int64_t* src, const int64_t
         DevBuf* b = k == 0 ? csc : csr;
         TRY(b[0].alloc((N + 1) * 4)); TRY(b[1].alloc(E * 4)); TRY(b[2].alloc(E * 4));
         TRY(b[3].alloc(hubcap)); TRY(b[4].alloc(hubcap)); TRY(b[5].alloc(N * 4));
-        int32_t counts[2];
+        TRY(b[6].alloc((size_t)stag_csx_items_capacity(E, N) * 16)); TRY(b[7].alloc(E * 4)); TRY(b[8].alloc(E * 4));
+        int32_t counts[3];
         TRYRC(stag_csx_build((const int64_t*)d_src.p, (const int64_t*)d_dst.p, E, N, k == 0, b[0].as<int32_t>(),
                              b[1].as<int32_t>(), b[2].as<int32_t>(), b[3].as<int32_t>(), b[4].as<int32_t>(),
-                             b[5].as<int32_t>(), counts,
+                             b[5].as<int32_t>(), b[6].as<int32_t>(), b[7].as<int32_t>(), b[8].as<int32_t>(), counts,
                              d_ws.p, cws, stream));
         G[k].num_rows = N; G[k].num_cols = N; G[k].num_edges = E;
         G[k].indptr = b[0].as<int32_t>(); G[k].indices = b[1].as<int32_t>(); G[k].eid = b[2].as<int32_t>();
         G[k].num_hubs = counts[0]; G[k].num_hub_segs = counts[1];
         G[k].hub_rows = b[3].as<int32_t>(); G[k].hub_seg_ptr = b[4].as<int32_t>();
         G[k].row_order = b[5].as<int32_t>();
+        G[k].items = b[6].as<int32_t>(); G[k].num_items = counts[2]; G[k].erow = b[7].as<int32_t>(); G[k].eidf = b[8].as<int32_t>();
       }
       const float *ss = nullptr, *ds = nullptr;
       if (gcn_norm_both) {

@@ -45,6 +45,12 @@ struct AggParams {
   const int32_t* hub_rows;
   const int32_t* hub_seg_ptr;
   const int32_t* row_order;  // rows in processing order (by degree), or null
+  const int32_t* items;      // stream items {row0, row1, e0, e1}
+  const int32_t* erow;       // row of every stored edge
+  const int32_t* eidf;       // edge id of every stored edge, bit 31 set on the last edge of its row
+  const int4* rec;           // per-call edge records (edge_record_kernel), workspace
+  int num_items;
+  uint32_t rk[2 * kPhiloxRounds];  // Philox round keys
   int num_hubs, num_hub_segs;
   int N;
   int64_t E;
@@ -55,7 +61,7 @@ struct AggParams {
   const float* rscale;
   float* out;
   int64_t ldo, out_ss;
-  int D, S, noct;
+  int D, S, nblk, dpad;  // nblk Philox blocks per row; dpad = D rounded up to whole 64-channel groups
   int lpr_log2;
   // column blocks: the channels are processed in ncb blocks of cw floats so that the gathered
   // operand of one block ([N, cw]) stays L2-resident; cb_major orders the blocks outermost
@@ -68,7 +74,7 @@ struct AggParams {
   const float* ext;
   PhiloxKey key;
   float* norm_scale_out;
-  // hub partial sums [S][num_hub_segs][noct*8]
+  // hub partial sums [S][num_hub_segs][dpad]
   float* part_acc;
   float* part_w;
   // gradient mode
@@ -77,20 +83,26 @@ struct AggParams {
   float* dp0;
   float* dp1;
   float* dw_ext;
-  float* dp_partial;  // [grid][2][noct*8]
+  float* dp_partial;  // [grid][2][dpad]
 };
+
+// Channel layout of a lane: Philox block b (= lane's index among the blocks of a row) owns the two
+// quads of channels starting at c = 64*(b/8) + 4*(b%8) and at c + 32, so that the 8 lanes of a
+// 64-channel group read two contiguous 128-byte lines with their two 128-bit loads (noise.cuh).
+__device__ __forceinline__ int chan(int c, int i) { return i < 4 ? c + i : c + 28 + i; }
+__device__ __forceinline__ int first_chan(int c0, int sl) { return c0 + ((sl >> 3) << 6) + ((sl & 7) << 2); }
 
 template <bool VEC>
 __device__ __forceinline__ void load8(const float* __restrict__ row, int c, int D, float (&v)[8]) {
   if (VEC) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (c < D) a = __ldg(reinterpret_cast<const float4*>(row + c));
-    if (c + 4 < D) b = __ldg(reinterpret_cast<const float4*>(row + c + 4));
+    if (c + 32 < D) b = __ldg(reinterpret_cast<const float4*>(row + c + 32));
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (c + i < D) ? __ldg(row + c + i) : 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = (chan(c, i) < D) ? __ldg(row + chan(c, i)) : 0.f;
   }
 }
 
@@ -102,15 +114,15 @@ __device__ __forceinline__ void store8(float* __restrict__ row, int c, int D, co
     const float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
     if (STREAM) {
       if (c < D) __stcs(reinterpret_cast<float4*>(row + c), a);
-      if (c + 4 < D) __stcs(reinterpret_cast<float4*>(row + c + 4), b);
+      if (c + 32 < D) __stcs(reinterpret_cast<float4*>(row + c + 32), b);
     } else {
       if (c < D) *reinterpret_cast<float4*>(row + c) = a;
-      if (c + 4 < D) *reinterpret_cast<float4*>(row + c + 4) = b;
+      if (c + 32 < D) *reinterpret_cast<float4*>(row + c + 32) = b;
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      if (c + i < D) row[c + i] = v[i];
+      if (chan(c, i) < D) row[chan(c, i)] = v[i];
   }
 }
 
@@ -151,9 +163,254 @@ __device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t 
   }
 }
 
+// ---- hot kernel ------------------------------------------------------------------------------
+// MODE 2 / PSH 0 without relu / in-norm / gradients (the arxiv_mle configuration, forward and
+// transposed): generated per-channel noise with scalar or per-edge parameters, gather scale folded
+// into the per-edge pair (A, B).
+//
+// Unit of work of a lane group: one STREAM ITEM = a range of consecutive rows holding about
+// kRangeEdges stored edges (StagGraph::items) or one hub segment.  The group walks the item's
+// edges as ONE contiguous stream: edge records (neighbour, edge id, folded parameters, row and row
+// scale) are fetched in coalesced batches of LPR one batch AHEAD of their use, the gathered rows
+// are staged through a per-lane shared-memory ring filled by cp.async (LDGSTS, RING_STAGES - 1
+// edges in flight, no registers held), and a row is written when the stream crosses into the next
+// one.  So the only latency a warp ever waits for is one ring fill per batch, every group of a
+// warp has the same trip count whatever the degree distribution, and a zero-degree row costs one
+// store.  A lane only reads ring slots it wrote itself: cp.async.wait_group orders them, no barrier.
+#ifndef STAG_RING_STAGES
+#define STAG_RING_STAGES 6
+#endif
+#ifndef STAG_STREAM_MINBLOCKS
+#define STAG_STREAM_MINBLOCKS 3
+#endif
+constexpr int RING_STAGES = STAG_RING_STAGES;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Philox with the round keys read straight from the kernel-parameter constant bank (AggParams::rk):
+// one LOP3 per key injection, no per-thread key schedule.
+__device__ __forceinline__ uint4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const AggParams& p) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < kPhiloxRounds; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0;
+    const uint64_t p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ p.rk[2 * r];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ p.rk[2 * r + 1];
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Per-call edge records of the streaming kernel: {neighbour, eid | last-of-row << 31, A, B} with BOTH
+// degree scalings (gather side and row side) and the distribution parameters folded into the pair
+// (A, B) (see folded_oct), so that the stream has no dependent loads and a row is finished by a plain
+// store.  Hub rows keep their row scale out of (A, B): hub_finalize_kernel applies it once.
+template <int KIND>
+__global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p.E) return;
+  const int idx = __ldg(p.indices + j);
+  const int ef = __ldg(p.eidf + j);
+  const int row = __ldg(p.erow + j);
+  float sc = p.gscale ? __ldg(p.gscale + idx) : 1.0f;
+  if (p.rscale && __ldg(p.indptr + row + 1) - __ldg(p.indptr + row) <= kHubThreshold) sc *= __ldg(p.rscale + row);
+  const int64_t pi = p.pshape >= STAG_PARAM_EDGE ? (ef & 0x7fffffff) : 0;
+  const float pa = __ldg(p.p0 + pi);
+  const float pb = KIND != STAG_NOISE_BERNOULLI ? __ldg(p.p1 + pi) : 0.f;
+  float a, b;
+  if (KIND == STAG_NOISE_NORMAL) { a = sc * pa; b = sc * pb; }
+  else if (KIND == STAG_NOISE_UNIFORM) { a = sc * pa; b = sc * (pb - pa); }
+  else { a = pa; b = sc; }
+  rec[j] = make_int4(idx, ef, __float_as_int(a), __float_as_int(b));
+}
+
+// rows without stored edges are not visited by the edge stream: write their zeros
+__global__ void zero_empty_rows_kernel(const AggParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = warp; v < p.N; v += nwarps) {
+    if (__ldg(p.indptr + v + 1) != __ldg(p.indptr + v)) continue;
+    for (int s = 0; s < p.S; ++s) {
+      float* o = p.out + (int64_t)s * p.out_ss + v * p.ldo;
+      for (int c = lane; c < p.D; c += 32) o[c] = 0.f;
+    }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream_kernel(const AggParams p) {
+  extern __shared__ float4 ring[];  // [AGG_WARPS][RING_STAGES][2][32]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int LPR = 1 << p.lpr_log2;
+  const int RPW = 32 >> p.lpr_log2;
+  const int sub = lane >> p.lpr_log2;
+  const int sl = lane & (LPR - 1);
+  const int D8 = p.dpad;
+  const uint32_t gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const float4* my_ring = ring + (size_t)warp * RING_STAGES * 64 + lane;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
+
+  const int n_items = p.num_hub_segs + p.num_items;
+  const int IG = (n_items + RPW - 1) / RPW;  // warp items per (sample, column block)
+  const int64_t total = (int64_t)IG * p.S * p.ncb;
+  const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+
+  for (int64_t item = (int64_t)blockIdx.x * AGG_WARPS + warp; item < total; item += total_warps) {
+    const int64_t outer = item / IG;
+    const int gi = (int)(item - outer * IG) * RPW + sub;
+    int s, cb;
+    if (p.cb_major) {
+      cb = (int)(outer / p.S);
+      s = (int)(outer - (int64_t)cb * p.S);
+    } else {
+      s = (int)(outer / p.ncb);
+      cb = (int)(outer - (int64_t)s * p.ncb);
+    }
+    const int c_begin = cb * p.cw;
+    const int c_end = min(c_begin + p.cw, D8);
+    // resolve the group's item: stored edges [e0, e1)
+    int e0 = 0, e1 = 0, part_slot = -1;
+    if (gi < p.num_hub_segs) {
+      int lo = 0, hi = p.num_hubs;  // last hub with hub_seg_ptr[h] <= gi
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.hub_seg_ptr + mid) <= gi) lo = mid; else hi = mid;
+      }
+      const int row = __ldg(p.hub_rows + lo);
+      const int k = gi - __ldg(p.hub_seg_ptr + lo);
+      e0 = __ldg(p.indptr + row) + k * kHubSegment;
+      e1 = min(e0 + kHubSegment, __ldg(p.indptr + row + 1));
+      part_slot = gi;
+    } else if (gi < n_items) {
+      const int4 it = __ldg(reinterpret_cast<const int4*>(p.items) + (gi - p.num_hub_segs));
+      e0 = it.z;
+      e1 = it.w >= 0 ? it.w : it.z;  // it.w < 0: placeholder of a hub row, nothing to do here
+    }
+    const int nedges = e1 - e0;
+    int maxn = nedges;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
+
+    const float* xs = p.x + (int64_t)s * p.x_ss;
+    float* outs = p.out + (int64_t)s * p.out_ss;
+    const uint32_t smp = (uint32_t)(p.sample_base + s);
+
+    for (int c0 = c_begin; c0 < c_end; c0 += max(LPR * 8, 64)) {
+      const int c = first_chan(c0, sl);
+      const bool qvalid = c < p.D && c < c_end;
+      const bool qvalid2 = qvalid && c + 32 < p.D;
+      const uint32_t oct = (uint32_t)((c0 >> 3) + sl);  // Philox block of this lane
+      const float* xc = xs + (qvalid ? c : 0);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+      // edge records of one batch, fetched one batch ahead: lane sl owns stream position off + sl
+      auto load_records = [&](int off, int4& rc, int& rw) {
+        rc = make_int4(0, 0, 0, 0);
+        rw = 0;
+        if (off + sl < nedges) {
+          rc = __ldg(p.rec + e0 + off + sl);
+          rw = __ldg(p.erow + e0 + off + sl);
+        }
+      };
+
+      int4 nx_rec;
+      int nx_row;
+      load_records(0, nx_rec, nx_row);
+      for (int off = 0; off < maxn; off += LPR) {
+        const int my_idx = nx_rec.x, my_ef = nx_rec.y, my_row = nx_row;
+        const float my_a = __int_as_float(nx_rec.z), my_b = __int_as_float(nx_rec.w);
+        load_records(off + LPR, nx_rec, nx_row);
+        const int cnt = min(LPR, maxn - off);
+        const int mylen = nedges - off;  // edges this group still has in this batch (may be <= 0)
+
+        auto issue = [&](int t) {
+          const int u = __shfl_sync(0xffffffffu, my_idx, t, LPR);
+          const float* src = xc + (int64_t)u * p.ldx;
+          const uint32_t dst = ring_s + (uint32_t)(t % RING_STAGES) * (64u * 16u);
+          const bool on = t < mylen;
+          cp_async16(dst, src, (on && qvalid) ? 16 : 0);  // src-size 0 -> zero fill
+          cp_async16(dst + 32u * 16u, src + 32, (on && qvalid2) ? 16 : 0);
+        };
+#pragma unroll
+        for (int t = 0; t < RING_STAGES - 1; ++t) {
+          if (t < cnt) issue(t);
+          cp_async_commit();
+        }
+        int st = 0;
+        for (int t = 0; t < cnt; ++t) {
+          if (t + RING_STAGES - 1 < cnt) issue(t + RING_STAGES - 1);
+          cp_async_commit();
+          const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
+          const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
+          const float B = __shfl_sync(0xffffffffu, my_b, t, LPR);
+          // weights of this oct with the gather scale folded in (see folded_oct)
+          float w[8];
+          {
+            const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), oct, smp, p.key.c3, p);
+            const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (KIND == STAG_NOISE_NORMAL) {
+                float rad, cs, sn;
+                bm_parts(q[i], rad, cs, sn);
+                const float rb = rad * B;
+                w[2 * i] = fmaf(cs, rb, A);
+                w[2 * i + 1] = fmaf(sn, rb, A);
+              } else if (KIND == STAG_NOISE_UNIFORM) {
+                w[2 * i] = fmaf(half_uniform<false>(q[i]), B, A);
+                w[2 * i + 1] = fmaf(half_uniform<true>(q[i]), B, A);
+              } else {
+                w[2 * i] = half_uniform<false>(q[i]) < A ? B : 0.f;
+                w[2 * i + 1] = half_uniform<true>(q[i]) < A ? B : 0.f;
+              }
+            }
+          }
+          cp_async_wait<RING_STAGES - 1>();
+          const float4 xa = my_ring[st * 64], xb = my_ring[st * 64 + 32];
+          st = st + 1 == RING_STAGES ? 0 : st + 1;
+          acc[0] = fmaf(w[0], xa.x, acc[0]);
+          acc[1] = fmaf(w[1], xa.y, acc[1]);
+          acc[2] = fmaf(w[2], xa.z, acc[2]);
+          acc[3] = fmaf(w[3], xa.w, acc[3]);
+          acc[4] = fmaf(w[4], xb.x, acc[4]);
+          acc[5] = fmaf(w[5], xb.y, acc[5]);
+          acc[6] = fmaf(w[6], xb.z, acc[6]);
+          acc[7] = fmaf(w[7], xb.w, acc[7]);
+          if (ef < 0 && part_slot < 0 && t < mylen) {  // last edge of its row: write the row (group-uniform)
+            const int rw = __shfl_sync(gmask, my_row, t, LPR);
+            if (qvalid) store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+          }
+        }
+      }
+      if (part_slot >= 0 && qvalid) {  // hub segment: its partial sum, combined by hub_finalize_kernel
+        const int64_t o = ((int64_t)s * p.num_hub_segs + part_slot) * D8;
+        store8<true, false>(p.part_acc + o, c, D8, acc);
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 template <int MODE, int KIND, int PSH, bool VEC, bool GRADS, bool FOLD>
 __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const AggParams p) {
-  extern __shared__ float smem[];  // param grads: [AGG_WARPS][2][noct*8]
+  extern __shared__ float smem[];  // param grads: [AGG_WARPS][2][dpad]
   constexpr int U = GRADS ? 1 : 2;  // edges in flight per lane
   constexpr bool GEN = MODE == 2;
   // parameter gradients exist for generated Normal / Uniform noise only
@@ -170,7 +427,7 @@ __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const Ag
   const int RPW = 32 >> p.lpr_log2;
   const int sub = lane >> p.lpr_log2;
   const int sl = lane & (LPR - 1);
-  const int D8 = p.noct * 8;
+  const int D8 = p.dpad;
 
   float* my_sm = nullptr;
   if (GRADS && dense_pg) {
@@ -236,10 +493,10 @@ __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const Ag
     const float rs = (row >= 0 && p.rscale) ? __ldg(p.rscale + row) : 1.0f;
     const uint32_t smp = (uint32_t)(p.sample_base + s);
 
-    for (int c0 = c_begin; c0 < c_end; c0 += LPR * 8) {
-      const int c = c0 + sl * 8;
+    for (int c0 = c_begin; c0 < c_end; c0 += max(LPR * 8, 64)) {
+      const int c = first_chan(c0, sl);
       const bool qvalid = c < p.D && c < c_end;
-      const uint32_t oct = (uint32_t)(c >> 3);
+      const uint32_t oct = (uint32_t)((c0 >> 3) + sl);  // Philox block of this lane
       float P0[8], P1[8];
       if (GEN && PSH == 1) {
         load8<VEC>(p.p0, c, p.D, P0);
@@ -479,9 +736,9 @@ __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const Ag
       if (row >= 0 && qvalid) {
         if (part_slot >= 0) {
           if (p.out) {
-            const int64_t o = ((int64_t)s * p.num_hub_segs + part_slot) * D8 + c;
-            store8<true, false>(p.part_acc + o, 0, 8, acc);
-            if (!GRADS && p.in_norm) store8<true, false>(p.part_w + o, 0, 8, wsum);
+            const int64_t o = ((int64_t)s * p.num_hub_segs + part_slot) * D8;
+            store8<true, false>(p.part_acc + o, c, D8, acc);
+            if (!GRADS && p.in_norm) store8<true, false>(p.part_w + o, c, D8, wsum);
           }
         } else if (p.out) {
           if (!GRADS && p.in_norm) {
@@ -531,8 +788,8 @@ __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const Ag
           if (sub == 0 && c < D8) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              my_sm[c + i] += d0[i];
-              my_sm[D8 + c + i] += d1[i];
+              my_sm[chan(c, i)] += d0[i];
+              my_sm[D8 + chan(c, i)] += d1[i];
             }
           }
         }
@@ -556,7 +813,7 @@ __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const Ag
 // Combine the partial sums of hub rows in segment order and finish the row.
 __global__ void hub_finalize_kernel(const AggParams p, int grads) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int D8 = p.noct * 8;
+  const int D8 = p.dpad;
   const int64_t total = (int64_t)p.S * p.num_hubs * p.D;
   if (idx >= total) return;
   const int c = (int)(idx % p.D);
@@ -624,29 +881,30 @@ __global__ void param_finalize_kernel(const float* __restrict__ partial, int nct
 // noise materialisation (compat path + RNG tests): w[s,e,c]
 template <int KIND>
 __global__ void emit_kernel(const AggParams p, float* __restrict__ w_out, float* __restrict__ eps_out) {
-  const int noct = p.noct;
-  const int64_t total = (int64_t)p.S * p.E * noct;
+  const int nblk = p.nblk;
+  const int64_t total = (int64_t)p.S * p.E * nblk;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % noct);
-    const int64_t e = (i / noct) % p.E;
-    const int s = (int)(i / ((int64_t)noct * p.E));
-    const int c = q * 8;
+    const int q = (int)(i % nblk);
+    const int64_t e = (i / nblk) % p.E;
+    const int s = (int)(i / ((int64_t)nblk * p.E));
+    const int c = first_chan(0, q);
     float raw[8];
     raw_oct<KIND>((uint32_t)e, (uint32_t)q, (uint32_t)(p.sample_base + s), p.key, raw);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (c + j < p.K) {
+      const int ch = chan(c, j);
+      if (ch < p.K) {
         int64_t pi;
         switch (p.pshape) {
           case STAG_PARAM_SCALAR: pi = 0; break;
-          case STAG_PARAM_CHANNEL: pi = c + j; break;
+          case STAG_PARAM_CHANNEL: pi = ch; break;
           case STAG_PARAM_EDGE: pi = e; break;
-          default: pi = e * p.K + c + j; break;
+          default: pi = e * p.K + ch; break;
         }
         float w = transform<KIND>(raw[j], p.p0[pi], p.p1 ? p.p1[pi] : 0.f);
         if (p.relu) w = fmaxf(w, 0.f);
-        const int64_t o = ((int64_t)s * p.E + e) * p.K + c + j;
+        const int64_t o = ((int64_t)s * p.E + e) * p.K + ch;
         w_out[o] = w;
         if (eps_out) eps_out[o] = raw[j];
       }
@@ -667,19 +925,27 @@ __global__ void segment_reduce_kernel(const float* __restrict__ feat, int64_t ld
   out[(int64_t)b * ldo + c] = acc;
 }
 
-static int lpr_log2_for(int noct) {
+// Philox blocks needed by `width` channels: 8 per whole 64-channel group, one per started quad of
+// the first half of the last group
+static int blocks_for(int width) {
+  const int rem = width % 64;
+  const int last = (rem + 3) / 4;
+  return 8 * (width / 64) + (last < 8 ? last : 8);
+}
+
+static int lpr_log2_for(int nblk) {
   int l = 0;
-  while ((1 << l) < noct && l < 5) ++l;
+  while ((1 << l) < nblk && l < 5) ++l;
   return l;
 }
 
 struct WsLayout {
-  size_t part_acc, part_w, dp_partial, total;
+  size_t part_acc, part_w, dp_partial, rec, total;
 };
 
 static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
   WsLayout L;
-  const size_t D8 = (size_t)((D + 7) / 8) * 8;
+  const size_t D8 = (size_t)((D + 63) / 64) * 64;
   size_t off = 0;
   L.part_acc = off;
   off += align_up((size_t)S * g->num_hub_segs * D8 * 4 + 16, 256);
@@ -687,6 +953,8 @@ static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
   off += align_up((size_t)S * g->num_hub_segs * D8 * 4 + 16, 256);
   L.dp_partial = off;
   off += align_up((size_t)grid_max * 2 * D8 * 4 + 16, 256);
+  L.rec = off;
+  off += align_up((size_t)g->num_edges * 16 + 16, 256);
   L.total = off;
   return L;
 }
@@ -732,8 +1000,26 @@ static int launch_vec(const AggParams& p, bool vec, int grid, size_t smem, cudaS
 
 template <int KIND, bool GRADS>
 static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
-  if (!GRADS && psh == 0 && !p.relu && !p.in_norm)
+  if (!GRADS && psh == 0 && !p.relu && !p.in_norm) {
+    if (vec && p.items && p.erow && p.eidf) {  // streaming hot kernel (128-bit rows)
+      const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * 64 * sizeof(float4);
+      STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ring_bytes));
+      const int RPW = 32 >> p.lpr_log2;
+      const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S * p.ncb;
+      const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
+      const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * STAG_STREAM_MINBLOCKS ? ctas : num_sms() * STAG_STREAM_MINBLOCKS));
+      if (p.E > 0) {
+        edge_record_kernel<KIND><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(p, const_cast<int4*>(p.rec));
+        STAG_LAUNCH_CHECK();
+      }
+      zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
+      agg_stream_kernel<KIND><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+      STAG_LAUNCH_CHECK();
+      return STAG_OK;
+    }
     return launch_vec<2, KIND, 0, false, true>(p, vec, grid, smem, stream);
+  }
   switch (psh) {
     case 0: return launch_vec<2, KIND, 0, GRADS>(p, vec, grid, smem, stream);
     case 1: return launch_vec<2, KIND, 1, GRADS>(p, vec, grid, smem, stream);
@@ -772,6 +1058,10 @@ static void fill_noise(AggParams& p, const StagNoise* n, int D) {
   p.p1 = n->p1;
   p.ext = n->external;
   p.key = make_key(n->seed, n->offset);
+  for (int r = 0; r < kPhiloxRounds; ++r) {
+    p.rk[2 * r] = p.key.k0 + (uint32_t)r * 0x9E3779B9u;
+    p.rk[2 * r + 1] = p.key.k1 + (uint32_t)r * 0xBB67AE85u;
+  }
 }
 
 static void fill_graph(AggParams& p, const StagGraph* g) {
@@ -781,6 +1071,10 @@ static void fill_graph(AggParams& p, const StagGraph* g) {
   p.hub_rows = g->hub_rows;
   p.hub_seg_ptr = g->hub_seg_ptr;
   p.row_order = g->row_order;
+  p.items = g->items;
+  p.erow = g->erow;
+  p.eidf = g->eidf;
+  p.num_items = (int)g->num_items;
   p.num_hubs = g->num_hubs;
   p.num_hub_segs = g->num_hub_segs;
   p.N = (int)g->num_rows;
@@ -806,20 +1100,21 @@ constexpr size_t kL2Operand = 40u << 20;
 static void set_shape(AggParams& p, int D, int S, int64_t gathered_rows, bool shared_operand, bool grads) {
   p.D = D;
   p.S = S;
-  p.noct = (D + 7) / 8;
-  const int D8 = p.noct * 8;
+  p.nblk = blocks_for(D);
+  p.dpad = (D + 63) / 64 * 64;
+  const int D8 = p.dpad;
   int ncb = 1;
   if (!grads) {
     const size_t bytes = (size_t)gathered_rows * D * 4;
     ncb = (int)((bytes + kL2Operand - 1) / kL2Operand);
     if (ncb < 1) ncb = 1;
   }
-  int cw = ((D8 + ncb - 1) / ncb + 31) / 32 * 32;  // whole 128-byte lines per gathered row
+  int cw = ((D8 + ncb - 1) / ncb + 63) / 64 * 64;  // whole 64-channel groups
   if (cw > D8) cw = D8;
   p.cw = cw;
   p.ncb = (D8 + cw - 1) / cw;
   p.cb_major = shared_operand && S > 1;
-  p.lpr_log2 = lpr_log2_for(cw / 8);
+  p.lpr_log2 = lpr_log2_for(blocks_for(D < cw ? D : cw));
 }
 
 static int agg_grid(const AggParams& p) {
@@ -854,7 +1149,7 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
   if (rc) return rc;
   if (g->num_rows == 0) return STAG_OK;
   const WsLayout L = ws_layout(g, D, S, grid_cap());
-  if (g->num_hub_segs > 0 && (!ws || ws_bytes < L.total)) {
+  if (!ws || ws_bytes < L.total) {
     set_error("stag_spmm_fwd: workspace %zu < required %zu", ws_bytes, L.total);
     return STAG_EWORKSPACE;
   }
@@ -866,10 +1161,9 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
   p.out = out; p.ldo = ldo; p.out_ss = out_sample_stride;
   set_shape(p, D, S, g->num_cols, x_sample_stride == 0, false);
   p.norm_scale_out = norm_scale_out;
-  if (g->num_hub_segs > 0) {
-    p.part_acc = (float*)((char*)ws + L.part_acc);
-    p.part_w = (float*)((char*)ws + L.part_w);
-  }
+  p.part_acc = (float*)((char*)ws + L.part_acc);
+  p.part_w = (float*)((char*)ws + L.part_w);
+  p.rec = (const int4*)((char*)ws + L.rec);
   bool vec = (D % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && (x_sample_stride % 4 == 0) &&
              (out_sample_stride % 4 == 0) && aligned16(x) && aligned16(out);
   if (noise->kind == STAG_NOISE_EXTERNAL && noise->K != 1) vec = vec && aligned16(noise->external);
@@ -942,7 +1236,7 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   if (param_grads && noise->param_shape != STAG_PARAM_SCALAR && noise->K != 1)
     vec = vec && aligned16(noise->p0) && aligned16(noise->p1) && aligned16(dparam0) && aligned16(dparam1);
   const int grid = agg_grid(p);
-  const size_t smem = (param_grads && !edge_params) ? (size_t)AGG_WARPS * 2 * p.noct * 8 * sizeof(float) : 0;
+  const size_t smem = (param_grads && !edge_params) ? (size_t)AGG_WARPS * 2 * p.dpad * sizeof(float) : 0;
   if (smem > 200 * 1024) {
     set_error("stag_spmm_bwd: D=%d too wide for the shared-memory parameter-gradient staging", D);
     return STAG_EUNSUPPORTED;
@@ -957,7 +1251,7 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   if (param_grads && !edge_params) {
     const int scalar = p.pshape == STAG_PARAM_SCALAR;
     const int blocks = scalar ? 1 : (D + 255) / 256;
-    param_finalize_kernel<<<blocks, 256, 0, stream>>>(p.dp_partial, grid, p.noct * 8, D, scalar, dparam0, dparam1);
+    param_finalize_kernel<<<blocks, 256, 0, stream>>>(p.dp_partial, grid, p.dpad, D, scalar, dparam0, dparam1);
     STAG_LAUNCH_CHECK();
   }
   return STAG_OK;
@@ -979,8 +1273,9 @@ extern "C" int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_
   p.E = num_edges;
   p.S = S;
   p.D = noise->K;
-  p.noct = (noise->K + 7) / 8;
-  const int64_t total = (int64_t)S * num_edges * p.noct;
+  p.nblk = blocks_for(noise->K);
+  p.dpad = (noise->K + 63) / 64 * 64;
+  const int64_t total = (int64_t)S * num_edges * p.nblk;
   const int64_t want = (total + 255) / 256;
   const int grid = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
   switch (noise->kind) {

@@ -53,6 +53,8 @@ class _Structure:
             if self.eid_map is not None and self.num_edges:
                 m = self.eid_map.to(device=self.device, dtype=torch.int32)
                 keep["eid"].copy_(m[keep["eid"].long()])
+                last = keep["eidf"] < 0
+                keep["eidf"].copy_(torch.where(last, keep["eid"] | -2147483648, keep["eid"]))
             self._csx[key] = (g, keep)
         return self._csx[key]
 
@@ -121,14 +123,17 @@ def build_csx(src, dst, num_nodes, by_dst):
         hub_rows = torch.empty(E // thr + 1, dtype=torch.int32, device=dev)
         hub_seg_ptr = torch.empty(E // thr + 2, dtype=torch.int32, device=dev)
         row_order = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+        items = torch.empty((lib.stag_csx_items_capacity(E, N), 4), dtype=torch.int32, device=dev)
+        erow = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        eidf = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         ws_bytes = lib.stag_csx_workspace_bytes(E, N)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        counts = (ctypes.c_int32 * 2)()
+        counts = (ctypes.c_int32 * 3)()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.stag_csx_build(
             src.data_ptr(), dst.data_ptr(), E, N, 1 if by_dst else 0,
             indptr.data_ptr(), indices.data_ptr(), eid.data_ptr(),
-            hub_rows.data_ptr(), hub_seg_ptr.data_ptr(), row_order.data_ptr(), counts,
+            hub_rows.data_ptr(), hub_seg_ptr.data_ptr(), row_order.data_ptr(), items.data_ptr(), erow.data_ptr(), eidf.data_ptr(), counts,
             ws.data_ptr(), ws_bytes, stream))
     g = _lib.StagGraph()
     g.num_rows, g.num_cols, g.num_edges = N, N, E
@@ -136,7 +141,9 @@ def build_csx(src, dst, num_nodes, by_dst):
     g.num_hubs, g.num_hub_segs = int(counts[0]), int(counts[1])
     g.hub_rows, g.hub_seg_ptr = hub_rows.data_ptr(), hub_seg_ptr.data_ptr()
     g.row_order = row_order.data_ptr() if N > 0 else None
-    keep = {"indptr": indptr, "indices": indices[:E], "eid": eid[:E], "row_order": row_order[:N],
+    g.items, g.num_items = (items.data_ptr(), int(counts[2])) if N > 0 else (None, 0)
+    g.erow, g.eidf = erow.data_ptr(), eidf.data_ptr()
+    keep = {"indptr": indptr, "indices": indices[:E], "eid": eid[:E], "row_order": row_order[:N], "items": items[:int(counts[2])], "erow": erow[:E], "eidf": eidf[:E],
             "hub_rows": hub_rows[:g.num_hubs], "hub_seg_ptr": hub_seg_ptr[:g.num_hubs + 1]}
     return g, keep
 

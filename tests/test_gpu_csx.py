@@ -32,6 +32,31 @@ def check(src, dst, n, lib):
         deg = np.minimum(np.diff(indptr.astype(np.int64)), lib.stag_hub_threshold() + 1)
         want = np.lexsort((np.arange(n), deg))[::-1]
         assert np.array_equal(t["row_order"], want.astype(np.int32))
+        assert np.array_equal(t["erow"], np.repeat(np.arange(n, dtype=np.int32), np.diff(indptr)))
+        last = np.zeros(len(src), bool)
+        last[indptr[1:][np.diff(indptr) > 0] - 1] = True
+        assert np.array_equal(t["eidf"].view(np.uint32), eid.astype(np.uint32) | (last.astype(np.uint32) << 31))
+        # stream items: a partition of the rows into consecutive ranges, hubs isolated, stored by
+        # decreasing edge count (ties by decreasing first row)
+        it = t["items"]
+        if len(it):
+            cnt = np.where(it[:, 3] < 0, 0, it[:, 3] - it[:, 2])
+            assert np.array_equal(np.lexsort((it[:, 0], cnt))[::-1], np.arange(len(it)))
+            it = it[np.argsort(it[:, 0])]
+        assert g.num_items == len(it) <= lib.stag_csx_items_capacity(len(src), n)
+        if n:
+            ip = indptr.astype(np.int64)
+            assert it[0, 0] == 0 and it[-1, 1] == n
+            assert np.array_equal(it[1:, 0], it[:-1, 1]) and np.all(it[:, 1] > it[:, 0])
+            assert np.array_equal(it[:, 2], ip[it[:, 0]])
+            hub = np.diff(ip)[it[:, 0]] > lib.stag_hub_threshold()
+            assert np.all(it[hub, 3] == -1) and np.all(it[hub, 1] == it[hub, 0] + 1)
+            assert np.array_equal(it[~hub, 3], ip[it[~hub, 1]])
+            assert np.all(it[~hub, 3] - it[~hub, 2] < 64 + lib.stag_hub_threshold() + 1)
+            assert np.all(it[:, 1] - it[:, 0] <= 256)
+            inside = np.ones(n, bool)
+            inside[it[:, 0]] = False
+            assert not np.any((np.diff(ip) > lib.stag_hub_threshold()) & inside)
 
 
 @pytest.mark.parametrize("n,e", [(1, 0), (1, 7), (5, 0), (3, 9), (50, 300), (257, 4096), (1000, 4097),
@@ -80,6 +105,6 @@ def test_degrees_and_adj_tensors(lib):
 def test_csx_rejects_bad_arguments(lib):
     from stag_b200 import _lib
     import ctypes
-    counts = (ctypes.c_int32 * 2)()
-    rc = lib.stag_csx_build(0, 0, -1, 4, 1, 0, 0, 0, 0, 0, 0, counts, 0, 0, 0)
+    counts = (ctypes.c_int32 * 3)()
+    rc = lib.stag_csx_build(0, 0, -1, 4, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, counts, 0, 0, 0)
     assert rc == _lib.STAG_EINVAL and b"negative" in lib.stag_last_error()

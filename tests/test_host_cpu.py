@@ -29,7 +29,7 @@ def test_library_exports_every_header_symbol(lib):
 def test_struct_layout_matches_header():
     import ctypes
     from stag_b200 import _lib
-    assert ctypes.sizeof(_lib.StagGraph) == 80
+    assert ctypes.sizeof(_lib.StagGraph) == 112
     assert ctypes.sizeof(_lib.StagNoise) == 64
 
 
