@@ -116,6 +116,8 @@ typedef struct StagNoise {
 
 STAG_API const char* stag_last_error(void);
 STAG_API int stag_abi_version(void);
+/* number of CUDA kernels this library has launched since it was loaded (process-wide) */
+STAG_API long long stag_launch_count(void);
 STAG_API int stag_hub_threshold(void);
 STAG_API int stag_hub_segment(void);
 

@@ -55,6 +55,7 @@ _GP, _NP = ctypes.POINTER(StagGraph), ctypes.POINTER(StagNoise)
 SIGNATURES = {
     "stag_last_error": (ctypes.c_char_p, []),
     "stag_abi_version": (_I, []),
+    "stag_launch_count": (ctypes.c_longlong, []),
     "stag_hub_threshold": (_I, []),
     "stag_hub_segment": (_I, []),
     "stag_csx_workspace_bytes": (_SZ, [_I64, _I64]),

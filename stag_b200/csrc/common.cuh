@@ -9,6 +9,7 @@
 namespace stag {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // every kernel launch of the library is counted (stag_launch_count)
 
 #define STAG_CHECK_ARG(cond, ...)                 \
   do {                                            \
@@ -30,6 +31,7 @@ void set_error(const char* fmt, ...);
 
 #define STAG_LAUNCH_CHECK()                                                          \
   do {                                                                               \
+    ::stag::count_launch();                                                          \
     cudaError_t err__ = cudaGetLastError();                                          \
     if (err__ != cudaSuccess) {                                                      \
       ::stag::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__,             \

@@ -29,6 +29,7 @@
 // MODE 2  per-channel noise generated in registers; PSH 0: scalar or per-edge parameters
 //         (travel with the edge record, folded with the gather scale), 1: per-channel
 //         parameters in registers, 2: per-edge-per-channel parameters read from memory
+#include <stdlib.h>
 #include "common.cuh"
 #include "noise.cuh"
 
@@ -181,7 +182,7 @@ __device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t 
 #define STAG_RING_STAGES 6
 #endif
 #ifndef STAG_STREAM_MINBLOCKS
-#define STAG_STREAM_MINBLOCKS 3
+#define STAG_STREAM_MINBLOCKS 2
 #endif
 constexpr int RING_STAGES = STAG_RING_STAGES;
 
@@ -1095,7 +1096,7 @@ static int check_graph(const StagGraph* g, const char* who) {
 // rows of the gathered operand; blocks are only used when one [rows, D] operand does not fit the
 // part of L2 a gather can count on (kL2Operand), and never in gradient mode (per-edge outputs
 // are accumulated across channel chunks by one warp).
-constexpr size_t kL2Operand = 40u << 20;
+constexpr size_t kL2Operand = 96u << 20;
 
 static void set_shape(AggParams& p, int D, int S, int64_t gathered_rows, bool shared_operand, bool grads) {
   p.D = D;
@@ -1108,6 +1109,8 @@ static void set_shape(AggParams& p, int D, int S, int64_t gathered_rows, bool sh
     const size_t bytes = (size_t)gathered_rows * D * 4;
     ncb = (int)((bytes + kL2Operand - 1) / kL2Operand);
     if (ncb < 1) ncb = 1;
+    static const char* force = getenv("STAG_NCB");  // tuning knob: force the number of column blocks
+    if (force && atoi(force) > 0) ncb = atoi(force);
   }
   int cw = ((D8 + ncb - 1) / ncb + 63) / 64 * 64;  // whole 64-channel groups
   if (cw > D8) cw = D8;

@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -q -x > gpurun_out/test11.log 2>&1; echo "pytest exit $?" >> gpurun_out/test11.log
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench11.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:agg_stream -s 6 -c 2 -o gpurun_out/prof11 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu11.log 2>&1
+python -m pytest tests -m gpu -q -x > gpurun_out/test13.log 2>&1; echo "pytest exit $?" >> gpurun_out/test13.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench13.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke13.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke13.log
 echo done
