@@ -1,4 +1,5 @@
-python -m pytest tests -m gpu -q -x > gpurun_out/test13.log 2>&1; echo "pytest exit $?" >> gpurun_out/test13.log
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench13.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke13.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke13.log
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain14.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu14a.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain14b.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:agg_stream -s 18 -c 3 -o gpurun_out/r01_agg_stream python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu14b.log 2>&1
 echo done
