@@ -126,6 +126,7 @@ def run_reference(args, rank):
         return
     from oracle import cbuild, ref_c
     cbuild.build()
+    ref_c.use_all_cores()
     src, dst = synth_graph()
     rng = np.random.default_rng(1)
     x = rng.standard_normal((N_NODES, WIDTH)).astype(np.float32)
@@ -290,6 +291,7 @@ def e2e_leg(dev, src, dst, S, sample_base, steps, warmup, dist):
 def cpu_baseline(mode):
     from oracle import cbuild, ref_c
     cbuild.build()
+    ref_c.use_all_cores()
     src, dst = synth_graph()
     rng = np.random.default_rng(1)
     x = rng.standard_normal((N_NODES, WIDTH)).astype(np.float32)

@@ -20,6 +20,14 @@ def num_threads():
     return cbuild.load().ref_num_threads()
 
 
+def use_all_cores():
+    """OpenMP threads = every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cbuild.load().ref_set_num_threads(int(n))
+    return num_threads()
+
+
 def csx_build(src, dst, num_nodes, by_dst=True):
     lib = cbuild.load()
     src = np.ascontiguousarray(src, dtype=np.int64)
