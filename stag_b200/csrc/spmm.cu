@@ -54,6 +54,7 @@ struct AggParams {
   uint32_t rk[2 * kPhiloxRounds];  // Philox round keys
   int num_hubs, num_hub_segs;
   int N;
+  int64_t ncols;  // rows of the gathered operand
   int64_t E;
   // gathered operand (x[indices[j]]), its per-node scale, row-side scale
   const float* x;
@@ -179,15 +180,23 @@ __device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t 
 // warp has the same trip count whatever the degree distribution, and a zero-degree row costs one
 // store.  A lane only reads ring slots it wrote itself: cp.async.wait_group orders them, no barrier.
 #ifndef STAG_RING_STAGES
-#define STAG_RING_STAGES 6
+#define STAG_RING_STAGES 4
 #endif
 #ifndef STAG_STREAM_MINBLOCKS
 #define STAG_STREAM_MINBLOCKS 2
 #endif
+#ifndef STAG_STREAM_U
+#define STAG_STREAM_U 2
+#endif
 constexpr int RING_STAGES = STAG_RING_STAGES;
+constexpr int STREAM_U = STAG_STREAM_U;  // edges per ring stage, computed as independent chains
 
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+// 16-byte async copy global -> shared; `ignore` set: the source is not read and zeros are written
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool ignore) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tcp.async.cg.shared.global [%0], [%1], 16, p;\n\t}" ::"r"(dst_smem),
+      "l"(src), "r"((int)ignore)
+      : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -252,7 +261,7 @@ __global__ void zero_empty_rows_kernel(const AggParams p) {
 
 template <int KIND>
 __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream_kernel(const AggParams p) {
-  extern __shared__ float4 ring[];  // [AGG_WARPS][RING_STAGES][2][32]
+  extern __shared__ float4 ring[];  // [AGG_WARPS][RING_STAGES * STREAM_U][2][32]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int LPR = 1 << p.lpr_log2;
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
   const int sl = lane & (LPR - 1);
   const int D8 = p.dpad;
   const uint32_t gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-  const float4* my_ring = ring + (size_t)warp * RING_STAGES * 64 + lane;
+  const float4* my_ring = ring + (size_t)warp * RING_STAGES * STREAM_U * 64 + lane;
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
 
   const int n_items = p.num_hub_segs + p.num_items;
@@ -308,6 +317,7 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
     const float* xs = p.x + (int64_t)s * p.x_ss;
     float* outs = p.out + (int64_t)s * p.out_ss;
     const uint32_t smp = (uint32_t)(p.sample_base + s);
+    const uint32_t ldx32 = (uint32_t)p.ldx;
 
     for (int c0 = c_begin; c0 < c_end; c0 += max(LPR * 8, 64)) {
       const int c = first_chan(c0, sl);
@@ -339,65 +349,84 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
         const int cnt = min(LPR, maxn - off);
         const int mylen = nedges - off;  // edges this group still has in this batch (may be <= 0)
 
-        auto issue = [&](int t) {
-          const int u = __shfl_sync(0xffffffffu, my_idx, t, LPR);
-          const float* src = xc + (int64_t)u * p.ldx;
-          const uint32_t dst = ring_s + (uint32_t)(t % RING_STAGES) * (64u * 16u);
-          const bool on = t < mylen;
-          cp_async16(dst, src, (on && qvalid) ? 16 : 0);  // src-size 0 -> zero fill
-          cp_async16(dst + 32u * 16u, src + 32, (on && qvalid2) ? 16 : 0);
-        };
+        // stage i of the ring = the U consecutive edges i*U .. i*U+U-1 of this batch
+        auto issue_stage = [&](int i, int slot) {
 #pragma unroll
-        for (int t = 0; t < RING_STAGES - 1; ++t) {
-          if (t < cnt) issue(t);
+          for (int k = 0; k < STREAM_U; ++k) {
+            const int t = i * STREAM_U + k;
+            if (t < cnt) {  // warp-uniform
+              const uint32_t u = (uint32_t)__shfl_sync(0xffffffffu, my_idx, t, LPR);
+              const float* src = xc + u * ldx32;  // 32-bit row offset (checked by the launcher)
+              const uint32_t dst = ring_s + (uint32_t)(slot * STREAM_U + k) * (64u * 16u);
+              const bool off_row = t >= mylen;  // beyond this group's edges: zero fill
+              cp_async16(dst, src, off_row || !qvalid);
+              cp_async16(dst + 32u * 16u, src + 32, off_row || !qvalid2);
+            }
+          }
+        };
+        const int nstages = (cnt + STREAM_U - 1) / STREAM_U;
+#pragma unroll
+        for (int i = 0; i < RING_STAGES - 1; ++i) {
+          if (i < nstages) issue_stage(i, i);
           cp_async_commit();
         }
-        int st = 0;
-        for (int t = 0; t < cnt; ++t) {
-          if (t + RING_STAGES - 1 < cnt) issue(t + RING_STAGES - 1);
+        int st = 0;                 // ring stage consumed by this iteration
+        int fill = RING_STAGES - 1;  // ring stage filled by this iteration
+        for (int i = 0; i < nstages; ++i) {
+          if (i + RING_STAGES - 1 < nstages) issue_stage(i + RING_STAGES - 1, fill);
+          fill = fill + 1 == RING_STAGES ? 0 : fill + 1;
           cp_async_commit();
-          const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
-          const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
-          const float B = __shfl_sync(0xffffffffu, my_b, t, LPR);
-          // weights of this oct with the gather scale folded in (see folded_oct)
-          float w[8];
-          {
-            const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), oct, smp, p.key.c3, p);
+          // weights of the stage's edges (independent Philox / Box-Muller chains), gather scale folded in
+          int ef[STREAM_U];
+          float w[STREAM_U][8];
+#pragma unroll
+          for (int k = 0; k < STREAM_U; ++k) {
+            const int t = i * STREAM_U + k;
+            ef[k] = __shfl_sync(0xffffffffu, my_ef, t, LPR);
+            const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
+            const float B = __shfl_sync(0xffffffffu, my_b, t, LPR);
+            const uint4 r4 = philox_rk((uint32_t)(ef[k] & 0x7fffffff), oct, smp, p.key.c3, p);
             const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int j = 0; j < 4; ++j) {
               if (KIND == STAG_NOISE_NORMAL) {
                 float rad, cs, sn;
-                bm_parts(q[i], rad, cs, sn);
+                bm_parts(q[j], rad, cs, sn);
                 const float rb = rad * B;
-                w[2 * i] = fmaf(cs, rb, A);
-                w[2 * i + 1] = fmaf(sn, rb, A);
+                w[k][2 * j] = fmaf(cs, rb, A);
+                w[k][2 * j + 1] = fmaf(sn, rb, A);
               } else if (KIND == STAG_NOISE_UNIFORM) {
-                w[2 * i] = fmaf(half_uniform<false>(q[i]), B, A);
-                w[2 * i + 1] = fmaf(half_uniform<true>(q[i]), B, A);
+                w[k][2 * j] = fmaf(half_uniform<false>(q[j]), B, A);
+                w[k][2 * j + 1] = fmaf(half_uniform<true>(q[j]), B, A);
               } else {
-                w[2 * i] = half_uniform<false>(q[i]) < A ? B : 0.f;
-                w[2 * i + 1] = half_uniform<true>(q[i]) < A ? B : 0.f;
+                w[k][2 * j] = half_uniform<false>(q[j]) < A ? B : 0.f;
+                w[k][2 * j + 1] = half_uniform<true>(q[j]) < A ? B : 0.f;
               }
             }
           }
           cp_async_wait<RING_STAGES - 1>();
-          const float4 xa = my_ring[st * 64], xb = my_ring[st * 64 + 32];
-          st = st + 1 == RING_STAGES ? 0 : st + 1;
-          acc[0] = fmaf(w[0], xa.x, acc[0]);
-          acc[1] = fmaf(w[1], xa.y, acc[1]);
-          acc[2] = fmaf(w[2], xa.z, acc[2]);
-          acc[3] = fmaf(w[3], xa.w, acc[3]);
-          acc[4] = fmaf(w[4], xb.x, acc[4]);
-          acc[5] = fmaf(w[5], xb.y, acc[5]);
-          acc[6] = fmaf(w[6], xb.z, acc[6]);
-          acc[7] = fmaf(w[7], xb.w, acc[7]);
-          if (ef < 0 && part_slot < 0 && t < mylen) {  // last edge of its row: write the row (group-uniform)
-            const int rw = __shfl_sync(gmask, my_row, t, LPR);
-            if (qvalid) store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, acc);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+          for (int k = 0; k < STREAM_U; ++k) {
+            const int t = i * STREAM_U + k;
+            if (t < cnt) {  // warp-uniform
+              const float4 xa = my_ring[(st * STREAM_U + k) * 64], xb = my_ring[(st * STREAM_U + k) * 64 + 32];
+              acc[0] = fmaf(w[k][0], xa.x, acc[0]);
+              acc[1] = fmaf(w[k][1], xa.y, acc[1]);
+              acc[2] = fmaf(w[k][2], xa.z, acc[2]);
+              acc[3] = fmaf(w[k][3], xa.w, acc[3]);
+              acc[4] = fmaf(w[k][4], xb.x, acc[4]);
+              acc[5] = fmaf(w[k][5], xb.y, acc[5]);
+              acc[6] = fmaf(w[k][6], xb.z, acc[6]);
+              acc[7] = fmaf(w[k][7], xb.w, acc[7]);
+              if (ef[k] < 0 && part_slot < 0 && t < mylen) {  // last edge of its row: write it (group-uniform)
+                const int rw = __shfl_sync(gmask, my_row, t, LPR);
+                if (qvalid) store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, acc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+              }
+            }
           }
+          st = st + 1 == RING_STAGES ? 0 : st + 1;
         }
       }
       if (part_slot >= 0 && qvalid) {  // hub segment: its partial sum, combined by hub_finalize_kernel
@@ -1002,8 +1031,9 @@ static int launch_vec(const AggParams& p, bool vec, int grid, size_t smem, cudaS
 template <int KIND, bool GRADS>
 static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
   if (!GRADS && psh == 0 && !p.relu && !p.in_norm) {
-    if (vec && p.items && p.erow && p.eidf) {  // streaming hot kernel (128-bit rows)
-      const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * 64 * sizeof(float4);
+    // streaming hot kernel: 128-bit rows, row offsets of the gathered operand fit 32 bits
+    if (vec && p.items && p.erow && p.eidf && p.ncols * p.ldx < (1ll << 31)) {
+      const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * STREAM_U * 64 * sizeof(float4);
       STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)ring_bytes));
       const int RPW = 32 >> p.lpr_log2;
@@ -1079,6 +1109,7 @@ static void fill_graph(AggParams& p, const StagGraph* g) {
   p.num_hubs = g->num_hubs;
   p.num_hub_segs = g->num_hub_segs;
   p.N = (int)g->num_rows;
+  p.ncols = g->num_cols;
   p.E = g->num_edges;
 }
 

@@ -1,5 +1,4 @@
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain14.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu14a.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain14b.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:agg_stream -s 18 -c 3 -o gpurun_out/r01_agg_stream python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu14b.log 2>&1
+python -m pytest tests/test_gpu_rng.py tests/test_gpu_spmm.py -m gpu -q -x > gpurun_out/test16.log 2>&1; echo "pytest exit $?" >> gpurun_out/test16.log
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench16.log 2>&1
+STAG_B200_LIB=/root/repo/variants/lib_u2s4.so python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench16_u2s4.log 2>&1
 echo done
