@@ -392,3 +392,69 @@ class _SegmentReduce(torch.autograd.Function):
         if ctx.mean:
             go = go / bnn.to(go).clamp(min=1).unsqueeze(-1)
         return torch.repeat_interleave(go, bnn, dim=0).reshape(ctx.shape), None, None
+
+
+class _DenseTransform(torch.autograd.Function):
+    """out = act(row_scale * (a @ weight) + bias) on stag_gemm_tcgen05 (3xTF32, fp32 accuracy).
+    Backward: dA = g @ W^T through the same kernel, dW / dbias by torch reductions."""
+
+    @staticmethod
+    def forward(ctx, a, weight, row_scale, bias, relu):
+        _require_cuda(a, "feat")
+        lib = _lib.load()
+        dev = a.device
+        K, Nout = weight.shape
+        a2 = _c(a).reshape(-1, K)
+        wt = weight.detach().to(torch.float32).t().contiguous()          # [Nout, K]
+        M = a2.shape[0]
+        out = torch.empty((M, Nout), dtype=torch.float32, device=dev)
+        rs = None
+        if row_scale is not None:
+            rs = _c(row_scale).reshape(-1)
+            if rs.numel() != M:                                          # [N] scale shared by the S samples
+                rs = rs.repeat(M // rs.numel())
+        b = _c(bias)
+        with torch.cuda.device(dev):
+            _lib.check(lib.stag_gemm_tcgen05(a2.data_ptr(), K, wt.data_ptr(), K, M, Nout, K, _ptr(rs), _ptr(b),
+                                             1 if relu else 0, out.data_ptr(), Nout, 0, 0, _stream(dev)))
+        ctx.save_for_backward(a2, weight, rs, out if relu else None)
+        ctx.relu, ctx.a_shape, ctx.has_bias = relu, a.shape, bias is not None
+        return out.reshape(tuple(a.shape[:-1]) + (Nout,))
+
+    @staticmethod
+    def backward(ctx, g):
+        a2, weight, rs, out = ctx.saved_tensors
+        lib = _lib.load()
+        dev = g.device
+        K, Nout = weight.shape
+        g2 = g.to(torch.float32).reshape(-1, Nout)
+        if ctx.relu:
+            g2 = g2 * (out > 0)
+        gbias = g2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[3]) else None
+        if rs is not None:
+            g2 = g2 * rs.unsqueeze(-1)
+        g2 = g2.contiguous()
+        ga = gw = None
+        if ctx.needs_input_grad[0]:
+            ga = torch.empty((g2.shape[0], K), dtype=torch.float32, device=dev)
+            w = weight.detach().to(torch.float32).contiguous()           # "wt" of the transposed product is W itself
+            with torch.cuda.device(dev):
+                _lib.check(lib.stag_gemm_tcgen05(g2.data_ptr(), Nout, w.data_ptr(), Nout, g2.shape[0], K, Nout,
+                                                 0, 0, 0, ga.data_ptr(), K, 0, 0, _stream(dev)))
+            ga = ga.reshape(ctx.a_shape)
+        if ctx.needs_input_grad[1]:
+            gw = a2.t() @ g2
+        return ga, gw, None, gbias, None
+
+
+def dense_transform(a, weight, row_scale=None, bias=None, relu=False):
+    """``act(row_scale[:,None] * (a @ weight) + bias)`` with ``weight`` [K, Nout], Nout <= 256, on the
+    tcgen05 tensor-core kernel; wider outputs use torch.matmul (cuBLAS)."""
+    if weight.shape[1] > 256:
+        out = torch.matmul(a, weight)
+        if row_scale is not None:
+            out = out * row_scale.reshape((-1,) + (1,) * 1) if out.dim() == 2 else out * row_scale.unsqueeze(-1)
+        if bias is not None:
+            out = out + bias
+        return out.relu() if relu else out
+    return _DenseTransform.apply(a, weight, row_scale, bias, relu)

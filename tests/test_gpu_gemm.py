@@ -1,0 +1,67 @@
+"""GPU: stag_gemm_tcgen05 (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulator) against a float64
+matmul: fp32-level accuracy (<= 1e-5 relative, max-norm), fused row scale / bias / relu epilogue, ragged
+M / K / N, and gradients."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 8, 16), (127, 16, 7), (128, 32, 16), (129, 50, 40), (1000, 128, 128),
+                                   (5000, 128, 40), (300, 1433, 16), (4096, 256, 256), (777, 100, 121),
+                                   (64, 9, 16), (2049, 33, 200)])
+def test_matches_float64(M, K, N):
+    from stag_b200 import ops
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = torch.randn(K, N, generator=g).cuda()
+    out = ops.dense_transform(a, w)
+    ref = a.double() @ w.double()
+    assert out.shape == (M, N)
+    assert rel(out, ref) < 1e-5, rel(out, ref)
+
+
+def test_epilogue_and_batched_samples():
+    from stag_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    S, N, K, C = 3, 500, 64, 40
+    a = torch.randn(S, N, K, generator=g).cuda()
+    w = torch.randn(K, C, generator=g).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    rs = torch.rand(N, generator=g).cuda() + 0.5
+    out = ops.dense_transform(a, w, row_scale=rs, bias=b, relu=True)
+    ref = torch.relu((a.double() @ w.double()) * rs.double()[None, :, None] + b.double())
+    assert out.shape == (S, N, C)
+    assert rel(out, ref) < 1e-5
+
+
+def test_gradients():
+    from stag_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(700, 48, generator=g).cuda().requires_grad_(True)
+    w = torch.randn(48, 24, generator=g).cuda().requires_grad_(True)
+    b = torch.randn(24, generator=g).cuda().requires_grad_(True)
+    rs = (torch.rand(700, generator=g) + 0.5).cuda()
+    go = torch.randn(700, 24, generator=g).cuda()
+    ops.dense_transform(a, w, row_scale=rs, bias=b, relu=True).backward(go)
+    a2, w2, b2 = [t.detach().double().requires_grad_(True) for t in (a, w, b)]
+    torch.relu((a2 @ w2) * rs.double()[:, None] + b2).backward(go.double())
+    assert rel(a.grad, a2.grad) < 1e-5 and rel(w.grad, w2.grad) < 1e-5 and rel(b.grad, b2.grad) < 1e-5
+
+
+def test_unsupported_width_falls_to_cublas_in_python_only():
+    """Nout > 256 is refused by the C entry point (STAG_EUNSUPPORTED) and routed to torch.matmul above it."""
+    import ctypes
+    from stag_b200 import _lib, ops
+    lib = _lib.load()
+    a = torch.randn(10, 8).cuda()
+    wt = torch.randn(300, 8).cuda()
+    out = torch.empty(10, 300).cuda()
+    rc = lib.stag_gemm_tcgen05(a.data_ptr(), 8, wt.data_ptr(), 8, 10, 300, 8, 0, 0, 0, out.data_ptr(), 300, 0, 0, 0)
+    assert rc == _lib.STAG_EUNSUPPORTED
+    assert ops.dense_transform(a, wt.t().contiguous()).shape == (10, 300)
