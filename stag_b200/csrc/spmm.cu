@@ -227,7 +227,7 @@ __device__ __forceinline__ uint4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2
 // (A, B) (see folded_oct), so that the stream has no dependent loads and a row is finished by a plain
 // store.  Hub rows keep their row scale out of (A, B): hub_finalize_kernel applies it once.
 template <int KIND>
-__global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec) {
+__global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, int scales_only) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p.E) return;
   const int idx = __ldg(p.indices + j);
@@ -235,6 +235,10 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec) {
   const int row = __ldg(p.erow + j);
   float sc = p.gscale ? __ldg(p.gscale + idx) : 1.0f;
   if (p.rscale && __ldg(p.indptr + row + 1) - __ldg(p.indptr + row) <= kHubThreshold) sc *= __ldg(p.rscale + row);
+  if (scales_only) {  // gradient kernel: the parameters stay in registers, only the two scalings are folded
+    rec[j] = make_int4(idx, ef, __float_as_int(sc), 0);
+    return;
+  }
   const int64_t pi = p.pshape >= STAG_PARAM_EDGE ? (ef & 0x7fffffff) : 0;
   const float pa = __ldg(p.p0 + pi);
   const float pb = KIND != STAG_NOISE_BERNOULLI ? __ldg(p.p1 + pi) : 0.f;
@@ -436,6 +440,223 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
     }
   }
   cp_async_wait<0>();
+}
+
+// ---- streaming gradient kernel ---------------------------------------------------------------------
+// Transposed pass with noise-parameter gradients (vi = True) for generated per-channel Normal / Uniform
+// noise with scalar or per-channel parameters (the r1 / rc posteriors), D <= 256, no in-norm.  Rows are
+// SOURCE nodes (CSR), the gathered operand is dOut.  Same edge stream as agg_stream_kernel; per row it
+// keeps TWO sums over the out-edges,
+//     a0[c] = sum_e m_e,c * A_e * dout[v_e,c]          a1[c] = sum_e m_e,c * A_e * dout[v_e,c] * r_e,c
+// (A_e = dst_scale[v_e] * src_scale[u], r = eps or u regenerated from the edge id, m = relu mask), from
+// which everything follows at the end of the row without ever touching x inside the edge loop:
+//     dx[u,c]      = P0[c] * a0 + P1'[c] * a1            (P1' = scale, or high - low)
+//     d P0[c]     += x[u,c] * a0   (Uniform: x * (a0 - a1))      d P1[c] += x[u,c] * a1
+// The row of x needed at the end of a row is fetched by cp.async together with the row's last edge.
+template <int KIND>
+__global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const AggParams p) {
+  extern __shared__ float4 ring[];  // [AGG_WARPS][RING_STAGES][2 operands][2][32], then float staging
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int LPR = 1 << p.lpr_log2;
+  const int RPW = 32 >> p.lpr_log2;
+  const int sub = lane >> p.lpr_log2;
+  const int sl = lane & (LPR - 1);
+  const int D8 = p.dpad;
+  const uint32_t gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  // ring slot = [gathered row: 2 x 32 float4][x row: 2 x 32 float4]
+  const float4* my_ring = ring + (size_t)warp * RING_STAGES * 128 + lane;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
+  float* stage = reinterpret_cast<float*>(ring + (size_t)AGG_WARPS * RING_STAGES * 128);  // [AGG_WARPS][2][dpad]
+
+  const int n_items = p.num_hub_segs + p.num_items;
+  const int IG = (n_items + RPW - 1) / RPW;
+  const int64_t total = (int64_t)IG * p.S;
+  const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+
+  // this lane's channels (single chunk: dpad <= LPR * 8) and parameters
+  const int c = first_chan(0, sl);
+  const bool qvalid = c < p.D;
+  const bool qvalid2 = c + 32 < p.D;
+  const uint32_t blk = (uint32_t)sl;
+  float P0[8], P1[8], d0[8], d1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = chan(c, i);
+    const bool ok = ch < p.D;
+    const int64_t pi = p.pshape == STAG_PARAM_SCALAR ? 0 : (ok ? ch : 0);
+    P0[i] = __ldg(p.p0 + pi);
+    P1[i] = __ldg(p.p1 + pi);
+    if (KIND == STAG_NOISE_UNIFORM) P1[i] -= P0[i];  // w = low + u * (high - low)
+    d0[i] = d1[i] = 0.f;
+  }
+  const uint32_t ldx32 = (uint32_t)p.ldx, ldxr32 = (uint32_t)p.ldxr;
+
+  for (int64_t item = (int64_t)blockIdx.x * AGG_WARPS + warp; item < total; item += total_warps) {
+    const int s = (int)(item / IG);
+    const int gi = (int)(item - (int64_t)s * IG) * RPW + sub;
+    int e0 = 0, e1 = 0, part_slot = -1;
+    if (gi < p.num_hub_segs) {
+      int lo = 0, hi = p.num_hubs;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.hub_seg_ptr + mid) <= gi) lo = mid; else hi = mid;
+      }
+      const int row = __ldg(p.hub_rows + lo);
+      const int k = gi - __ldg(p.hub_seg_ptr + lo);
+      e0 = __ldg(p.indptr + row) + k * kHubSegment;
+      e1 = min(e0 + kHubSegment, __ldg(p.indptr + row + 1));
+      part_slot = gi;
+    } else if (gi < n_items) {
+      const int4 it = __ldg(reinterpret_cast<const int4*>(p.items) + (gi - p.num_hub_segs));
+      e0 = it.z;
+      e1 = it.w >= 0 ? it.w : it.z;
+    }
+    const int nedges = e1 - e0;
+    int maxn = nedges;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
+
+    const float* gs_ = p.x + (int64_t)s * p.x_ss + (qvalid ? c : 0);         // gathered operand (dOut), lane's column
+    const float* xr_ = p.xrow + (int64_t)s * p.xr_ss + (qvalid ? c : 0);     // the rows' own features
+    float* outs = p.out ? p.out + (int64_t)s * p.out_ss : nullptr;
+    const uint32_t smp = (uint32_t)(p.sample_base + s);
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+
+    // records: {neighbour, eid | flush << 31, A, -}; flush = last edge of its row, or of a hub segment
+    auto load_records = [&](int off, int4& rc, int& rw) {
+      rc = make_int4(0, 0, 0, 0);
+      rw = 0;
+      if (off + sl < nedges) {
+        rc = __ldg(p.rec + e0 + off + sl);
+        rw = __ldg(p.erow + e0 + off + sl);
+        if (part_slot >= 0) rc.y = (rc.y & 0x7fffffff) | (off + sl == nedges - 1 ? (int)0x80000000 : 0);
+      }
+    };
+    int4 nx_rec;
+    int nx_row;
+    load_records(0, nx_rec, nx_row);
+    for (int off = 0; off < maxn; off += LPR) {
+      const int my_idx = nx_rec.x, my_ef = nx_rec.y, my_row = nx_row;
+      const float my_a = __int_as_float(nx_rec.z);
+      load_records(off + LPR, nx_rec, nx_row);
+      const int cnt = min(LPR, maxn - off);
+      const int mylen = nedges - off;
+
+      auto issue = [&](int t, int slot) {
+        const uint32_t u = (uint32_t)__shfl_sync(0xffffffffu, my_idx, t, LPR);
+        const int eft = __shfl_sync(0xffffffffu, my_ef, t, LPR);
+        const uint32_t rw = (uint32_t)__shfl_sync(0xffffffffu, my_row, t, LPR);
+        const float* src = gs_ + u * ldx32;
+        const uint32_t dst = ring_s + (uint32_t)slot * (128u * 16u);
+        const bool off_row = t >= mylen;
+        cp_async16(dst, src, off_row || !qvalid);
+        cp_async16(dst + 32u * 16u, src + 32, off_row || !qvalid2);
+        if (eft < 0 && !off_row) {  // the row ends with this edge: fetch its own feature row as well
+          const float* xs = xr_ + rw * ldxr32;
+          cp_async16(dst + 64u * 16u, xs, !qvalid);
+          cp_async16(dst + 96u * 16u, xs + 32, !qvalid2);
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < RING_STAGES - 1; ++i) {
+        if (i < cnt) issue(i, i);
+        cp_async_commit();
+      }
+      int st = 0, fill = RING_STAGES - 1;
+      for (int t = 0; t < cnt; ++t) {
+        if (t + RING_STAGES - 1 < cnt) issue(t + RING_STAGES - 1, fill);
+        fill = fill + 1 == RING_STAGES ? 0 : fill + 1;
+        cp_async_commit();
+        const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
+        const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
+        float raw[8];
+        {
+          const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk, smp, p.key.c3, p);
+          const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (KIND == STAG_NOISE_NORMAL) {
+              float rad, cs, sn;
+              bm_parts(q[j], rad, cs, sn);
+              raw[2 * j] = rad * cs;
+              raw[2 * j + 1] = rad * sn;
+            } else {
+              raw[2 * j] = half_uniform<false>(q[j]);
+              raw[2 * j + 1] = half_uniform<true>(q[j]);
+            }
+          }
+        }
+        cp_async_wait<RING_STAGES - 1>();
+        const float4 xa = my_ring[st * 128], xb = my_ring[st * 128 + 32];
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float y = A * xv[i];
+          if (p.relu && !(fmaf(raw[i], P1[i], P0[i]) > 0.f)) y = 0.f;
+          a0[i] += y;
+          a1[i] = fmaf(raw[i], y, a1[i]);
+        }
+        if (ef < 0 && t < mylen) {  // end of the row (or of the hub segment): group-uniform
+          const int rw = __shfl_sync(gmask, my_row, t, LPR);
+          const float4 ra = my_ring[st * 128 + 64], rb = my_ring[st * 128 + 96];
+          float xr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+          float dxv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dxv[i] = fmaf(P1[i], a1[i], P0[i] * a0[i]);
+          if (part_slot >= 0) {
+            // hub segment: dx partial (row scale applied by hub_finalize_kernel); x scaled here
+            const float rs = p.rscale ? __ldg(p.rscale + rw) : 1.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xr[i] *= rs;
+            if (outs && qvalid) store8<true, false>(p.part_acc + ((int64_t)s * p.num_hub_segs + part_slot) * D8, c, D8, dxv);
+          } else if (outs && qvalid) {
+            store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, dxv);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float t1 = xr[i] * a1[i];
+            d1[i] += t1;
+            d0[i] += KIND == STAG_NOISE_NORMAL ? xr[i] * a0[i] : xr[i] * a0[i] - t1;
+            a0[i] = a1[i] = 0.f;
+          }
+        }
+        st = st + 1 == RING_STAGES ? 0 : st + 1;
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- parameter-gradient partials: groups of a warp -> warp slice -> CTA row of dp_partial -----------
+  for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      d0[i] += __shfl_xor_sync(0xffffffffu, d0[i], o);
+      d1[i] += __shfl_xor_sync(0xffffffffu, d1[i], o);
+    }
+  }
+  float* my_stage = stage + (size_t)warp * 2 * D8;
+  for (int i = lane; i < 2 * D8; i += 32) my_stage[i] = 0.f;
+  __syncwarp();
+  if (sub == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (chan(c, i) < D8) {
+        my_stage[chan(c, i)] = d0[i];
+        my_stage[D8 + chan(c, i)] = d1[i];
+      }
+    }
+  }
+  __syncthreads();
+  float* dst = p.dp_partial + (size_t)blockIdx.x * 2 * D8;
+  for (int i = threadIdx.x; i < 2 * D8; i += AGG_THREADS) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < AGG_WARPS; ++w) v += stage[(size_t)w * 2 * D8 + i];
+    dst[i] = v;
+  }
 }
 
 template <int MODE, int KIND, int PSH, bool VEC, bool GRADS, bool FOLD>
@@ -1041,10 +1262,11 @@ static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t sm
       const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
       const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * STAG_STREAM_MINBLOCKS ? ctas : num_sms() * STAG_STREAM_MINBLOCKS));
       if (p.E > 0) {
-        edge_record_kernel<KIND><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(p, const_cast<int4*>(p.rec));
+        edge_record_kernel<KIND><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(p, const_cast<int4*>(p.rec), 0);
         STAG_LAUNCH_CHECK();
       }
       zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
+      STAG_LAUNCH_CHECK();
       agg_stream_kernel<KIND><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
       STAG_LAUNCH_CHECK();
       return STAG_OK;
@@ -1275,8 +1497,41 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
     set_error("stag_spmm_bwd: D=%d too wide for the shared-memory parameter-gradient staging", D);
     return STAG_EUNSUPPORTED;
   }
-  rc = launch_agg<true>(p, vec, grid, smem, stream);
-  if (rc) return rc;
+  // streaming gradient kernel: generated per-channel Normal / Uniform noise, scalar or per-channel
+  // parameters, one channel chunk (D <= 256), 128-bit rows, 32-bit row offsets
+  const bool stream_ok = param_grads && !edge_params && noise->K == D && vec && p.items && p.erow && p.eidf &&
+                         p.dpad <= 256 && p.ncols * p.ldx < (1ll << 31) && (int64_t)p.N * p.ldxr < (1ll << 31);
+  int sgrid = grid;
+  if (stream_ok) {
+    p.rec = (const int4*)((char*)ws + L.rec);
+    const int RPW = 32 >> p.lpr_log2;
+    const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S;
+    const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
+    sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * 2 ? ctas : num_sms() * 2));
+    const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * 128 * sizeof(float4) + smem;
+    if (p.E > 0) {
+      edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
+          p, const_cast<int4*>(p.rec), 1);
+      STAG_LAUNCH_CHECK();
+    }
+    if (dx) {
+      zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
+      STAG_LAUNCH_CHECK();
+    }
+    if (noise->kind == STAG_NOISE_NORMAL) {
+      STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<STAG_NOISE_NORMAL>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+      agg_stream_grads_kernel<STAG_NOISE_NORMAL><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+    } else {
+      STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<STAG_NOISE_UNIFORM>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+      agg_stream_grads_kernel<STAG_NOISE_UNIFORM><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+    }
+    STAG_LAUNCH_CHECK();
+  } else {
+    rc = launch_agg<true>(p, vec, grid, smem, stream);
+    if (rc) return rc;
+  }
   if (g->num_hubs > 0 && dx) {
     const int64_t total = (int64_t)S * g->num_hubs * D;
     hub_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, 1);
@@ -1285,7 +1540,8 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   if (param_grads && !edge_params) {
     const int scalar = p.pshape == STAG_PARAM_SCALAR;
     const int blocks = scalar ? 1 : (D + 255) / 256;
-    param_finalize_kernel<<<blocks, 256, 0, stream>>>(p.dp_partial, grid, p.dpad, D, scalar, dparam0, dparam1);
+    param_finalize_kernel<<<blocks, 256, 0, stream>>>(p.dp_partial, stream_ok ? sgrid : grid, p.dpad, D, scalar, dparam0,
+                                                     dparam1);
     STAG_LAUNCH_CHECK();
   }
   return STAG_OK;

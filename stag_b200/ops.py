@@ -399,13 +399,17 @@ class _DenseTransform(torch.autograd.Function):
     Backward: dA = g @ W^T through the same kernel, dW / dbias by torch reductions."""
 
     @staticmethod
-    def forward(ctx, a, weight, row_scale, bias, relu):
+    def forward(ctx, a, weight, row_scale, bias, relu, transposed):
         _require_cuda(a, "feat")
         lib = _lib.load()
         dev = a.device
-        K, Nout = weight.shape
+        if transposed:      # weight given as [Nout, K] (torch.nn.Linear layout): already W^T
+            Nout, K = weight.shape
+            wt = weight.detach().to(torch.float32).contiguous()
+        else:               # weight [K, Nout] (GraphConv layout)
+            K, Nout = weight.shape
+            wt = weight.detach().to(torch.float32).t().contiguous()      # [Nout, K]
         a2 = _c(a).reshape(-1, K)
-        wt = weight.detach().to(torch.float32).t().contiguous()          # [Nout, K]
         M = a2.shape[0]
         out = torch.empty((M, Nout), dtype=torch.float32, device=dev)
         rs = None
@@ -418,7 +422,7 @@ class _DenseTransform(torch.autograd.Function):
             _lib.check(lib.stag_gemm_tcgen05(a2.data_ptr(), K, wt.data_ptr(), K, M, Nout, K, _ptr(rs), _ptr(b),
                                              1 if relu else 0, out.data_ptr(), Nout, 0, 0, _stream(dev)))
         ctx.save_for_backward(a2, weight, rs, out if relu else None)
-        ctx.relu, ctx.a_shape, ctx.has_bias = relu, a.shape, bias is not None
+        ctx.relu, ctx.a_shape, ctx.has_bias, ctx.transposed = relu, a.shape, bias is not None, transposed
         return out.reshape(tuple(a.shape[:-1]) + (Nout,))
 
     @staticmethod
@@ -426,7 +430,7 @@ class _DenseTransform(torch.autograd.Function):
         a2, weight, rs, out = ctx.saved_tensors
         lib = _lib.load()
         dev = g.device
-        K, Nout = weight.shape
+        Nout, K = weight.shape if ctx.transposed else weight.shape[::-1]
         g2 = g.to(torch.float32).reshape(-1, Nout)
         if ctx.relu:
             g2 = g2 * (out > 0)
@@ -437,24 +441,28 @@ class _DenseTransform(torch.autograd.Function):
         ga = gw = None
         if ctx.needs_input_grad[0]:
             ga = torch.empty((g2.shape[0], K), dtype=torch.float32, device=dev)
-            w = weight.detach().to(torch.float32).contiguous()           # "wt" of the transposed product is W itself
+            # the "W^T" operand of the transposed product dA = g @ W^T is W [K, Nout] itself
+            w = weight.detach().to(torch.float32)
+            w = (w.t() if ctx.transposed else w).contiguous()
             with torch.cuda.device(dev):
                 _lib.check(lib.stag_gemm_tcgen05(g2.data_ptr(), Nout, w.data_ptr(), Nout, g2.shape[0], K, Nout,
                                                  0, 0, 0, ga.data_ptr(), K, 0, 0, _stream(dev)))
             ga = ga.reshape(ctx.a_shape)
         if ctx.needs_input_grad[1]:
-            gw = a2.t() @ g2
-        return ga, gw, None, gbias, None
+            gw = (g2.t() @ a2) if ctx.transposed else (a2.t() @ g2)
+        return ga, gw, None, gbias, None, None
 
 
-def dense_transform(a, weight, row_scale=None, bias=None, relu=False):
-    """``act(row_scale[:,None] * (a @ weight) + bias)`` with ``weight`` [K, Nout], Nout <= 256, on the
-    tcgen05 tensor-core kernel; wider outputs use torch.matmul (cuBLAS)."""
-    if weight.shape[1] > 256:
-        out = torch.matmul(a, weight)
+def dense_transform(a, weight, row_scale=None, bias=None, relu=False, transposed=False):
+    """``act(row_scale[:,None] * (a @ W) + bias)`` on the tcgen05 tensor-core kernel (3xTF32, fp32-level
+    accuracy).  ``weight`` is W [K, Nout] (GraphConv layout) or, with ``transposed=True``, W^T [Nout, K]
+    (torch.nn.Linear layout).  Nout > 256 uses torch.matmul (cuBLAS)."""
+    nout = weight.shape[0] if transposed else weight.shape[1]
+    if nout > 256:
+        out = torch.matmul(a, weight.t() if transposed else weight)
         if row_scale is not None:
             out = out * row_scale.reshape((-1,) + (1,) * 1) if out.dim() == 2 else out * row_scale.unsqueeze(-1)
         if bias is not None:
             out = out + bias
         return out.relu() if relu else out
-    return _DenseTransform.apply(a, weight, row_scale, bias, relu)
+    return _DenseTransform.apply(a, weight, row_scale, bias, relu, transposed)

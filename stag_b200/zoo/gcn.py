@@ -5,7 +5,8 @@ Reference forward: src-norm (out_deg^-1/2, :67-75) -> ``update_all(u_mul_e, sum)
 -> ``@ W`` (:97-98) -> dst-norm (in_deg^-1/2, :100-108) -> bias (:110-111) -> activation
 (:113-114).  Here the two degree scalings and the noise live inside the aggregation kernel
 (``stag_spmm_fwd``), so one launch replaces the reference's ~10.  The dst-norm is a per-row
-scalar and commutes with ``@ W``; it is applied in the aggregation epilogue.
+scalar and commutes with ``@ W``; it is applied in the aggregation epilogue.  ``@ W`` + bias + relu
+run on the tcgen05 tensor-core kernel (``stag_gemm_tcgen05``, 3xTF32).
 """
 import torch
 from torch import nn
@@ -75,7 +76,12 @@ class GCN(nn.Module):
         rst = ops.stochastic_aggregate(g, feat, edge_weight, reduce="sum", src_scale=src_scale,
                                        dst_scale=dst_scale, n_samples=n_samples)
         if weight is not None:
-            rst = torch.matmul(rst, weight)
+            # agg @ W + bias (+ relu) in one tcgen05 kernel; other activations are applied after it
+            relu = self._activation in (torch.relu, torch.nn.functional.relu) or isinstance(self._activation, nn.ReLU)
+            rst = ops.dense_transform(rst, weight, bias=self.bias, relu=relu)
+            if self._activation is not None and not relu:
+                rst = self._activation(rst)
+            return rst
         if self.bias is not None:
             rst = rst + self.bias
         if self._activation is not None:

@@ -50,11 +50,12 @@ class GraphSAGE(nn.Module):
         n_samples = ops.spec_samples(edge_weight, feat)
         if self._aggre_type == "mean":
             h_neigh = ops.stochastic_aggregate(g, feat, edge_weight, reduce="mean", n_samples=n_samples)
-            rst = self.fc_self(feat) + self.fc_neigh(h_neigh)
+            rst = ops.dense_transform(feat, self.fc_self.weight, transposed=True) + \
+                ops.dense_transform(h_neigh, self.fc_neigh.weight, transposed=True)
         else:  # gcn
             neigh = ops.stochastic_aggregate(g, feat, edge_weight, reduce="sum", n_samples=n_samples)
             inv1 = st.scale(True, "inv1").unsqueeze(-1)
-            rst = self.fc_neigh((neigh + feat) * inv1)
+            rst = ops.dense_transform((neigh + feat) * inv1, self.fc_neigh.weight, transposed=True)
         if self.bias is not None:
             rst = rst + self.bias
         if self.activation is not None:
