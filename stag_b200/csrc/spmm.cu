@@ -453,7 +453,11 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
 //     dx[u,c]      = P0[c] * a0 + P1'[c] * a1            (P1' = scale, or high - low)
 //     d P0[c]     += x[u,c] * a0   (Uniform: x * (a0 - a1))      d P1[c] += x[u,c] * a1
 // The row of x needed at the end of a row is fetched by cp.async together with the row's last edge.
-template <int KIND>
+// The same kernel serves two more cases (template switches):
+//   PG = false           the two-sum FORWARD for per-channel parameters (or relu): out = P0*a0 + P1'*a1
+//   BODY = 1 (PG false)  per-edge weights (no noise / external [E,1] / generated K == 1 with scalar
+//                        parameters): the lane that loads an edge record computes its weight, out = a0
+template <int KIND, int BODY, bool PG>
 __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const AggParams p) {
   extern __shared__ float4 ring[];  // [AGG_WARPS][RING_STAGES][2 operands][2][32], then float staging
   const int lane = threadIdx.x & 31;
@@ -485,9 +489,9 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
     const int ch = chan(c, i);
     const bool ok = ch < p.D;
     const int64_t pi = p.pshape == STAG_PARAM_SCALAR ? 0 : (ok ? ch : 0);
-    P0[i] = __ldg(p.p0 + pi);
-    P1[i] = __ldg(p.p1 + pi);
-    if (KIND == STAG_NOISE_UNIFORM) P1[i] -= P0[i];  // w = low + u * (high - low)
+    P0[i] = BODY == 0 ? __ldg(p.p0 + pi) : 1.0f;
+    P1[i] = BODY == 0 ? __ldg(p.p1 + pi) : 0.0f;
+    if (BODY == 0 && KIND == STAG_NOISE_UNIFORM) P1[i] -= P0[i];  // w = low + u * (high - low)
     d0[i] = d1[i] = 0.f;
   }
   const uint32_t ldx32 = (uint32_t)p.ldx, ldxr32 = (uint32_t)p.ldxr;
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
     for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
 
     const float* gs_ = p.x + (int64_t)s * p.x_ss + (qvalid ? c : 0);         // gathered operand (dOut), lane's column
-    const float* xr_ = p.xrow + (int64_t)s * p.xr_ss + (qvalid ? c : 0);     // the rows' own features
+    const float* xr_ = PG ? p.xrow + (int64_t)s * p.xr_ss + (qvalid ? c : 0) : nullptr;  // the rows' own features
     float* outs = p.out ? p.out + (int64_t)s * p.out_ss : nullptr;
     const uint32_t smp = (uint32_t)(p.sample_base + s);
     float a0[8], a1[8];
@@ -533,6 +537,18 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
         rc = __ldg(p.rec + e0 + off + sl);
         rw = __ldg(p.erow + e0 + off + sl);
         if (part_slot >= 0) rc.y = (rc.y & 0x7fffffff) | (off + sl == nedges - 1 ? (int)0x80000000 : 0);
+        if (BODY == 1 && p.kind != STAG_NOISE_NONE) {  // per-edge weight of this (edge, sample), folded into A
+          const int eid = rc.y & 0x7fffffff;
+          float w;
+          if (p.kind == STAG_NOISE_EXTERNAL) {
+            w = __ldg(p.ext + (int64_t)s * p.E + eid);
+          } else {
+            w = transform_rt(p.kind, raw_first(p.kind, (uint32_t)eid, smp, p.key), __ldg(p.p0),
+                             p.p1 ? __ldg(p.p1) : 0.f);
+          }
+          if (p.relu) w = fmaxf(w, 0.f);
+          rc.z = __float_as_int(__int_as_float(rc.z) * w);
+        }
       }
     };
     int4 nx_rec;
@@ -554,7 +570,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
         const bool off_row = t >= mylen;
         cp_async16(dst, src, off_row || !qvalid);
         cp_async16(dst + 32u * 16u, src + 32, off_row || !qvalid2);
-        if (eft < 0 && !off_row) {  // the row ends with this edge: fetch its own feature row as well
+        if (PG && eft < 0 && !off_row) {  // the row ends with this edge: fetch its own feature row as well
           const float* xs = xr_ + rw * ldxr32;
           cp_async16(dst + 64u * 16u, xs, !qvalid);
           cp_async16(dst + 96u * 16u, xs + 32, !qvalid2);
@@ -573,7 +589,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
         const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
         const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
         float raw[8];
-        {
+        if (BODY == 0) {
           const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk, smp, p.key.c3, p);
           const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
@@ -594,32 +610,44 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
         const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float y = A * xv[i];
-          if (p.relu && !(fmaf(raw[i], P1[i], P0[i]) > 0.f)) y = 0.f;
-          a0[i] += y;
-          a1[i] = fmaf(raw[i], y, a1[i]);
+          if (BODY == 1) {
+            a0[i] = fmaf(A, xv[i], a0[i]);
+          } else {
+            float y = A * xv[i];
+            if (p.relu && !(fmaf(raw[i], P1[i], P0[i]) > 0.f)) y = 0.f;
+            a0[i] += y;
+            a1[i] = fmaf(raw[i], y, a1[i]);
+          }
         }
         if (ef < 0 && t < mylen) {  // end of the row (or of the hub segment): group-uniform
           const int rw = __shfl_sync(gmask, my_row, t, LPR);
-          const float4 ra = my_ring[st * 128 + 64], rb = my_ring[st * 128 + 96];
-          float xr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+          float xr[8];
+          if (PG) {
+            const float4 ra = my_ring[st * 128 + 64], rb = my_ring[st * 128 + 96];
+            xr[0] = ra.x; xr[1] = ra.y; xr[2] = ra.z; xr[3] = ra.w;
+            xr[4] = rb.x; xr[5] = rb.y; xr[6] = rb.z; xr[7] = rb.w;
+          }
           float dxv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dxv[i] = fmaf(P1[i], a1[i], P0[i] * a0[i]);
+          for (int i = 0; i < 8; ++i) dxv[i] = BODY == 1 ? a0[i] : fmaf(P1[i], a1[i], P0[i] * a0[i]);
           if (part_slot >= 0) {
-            // hub segment: dx partial (row scale applied by hub_finalize_kernel); x scaled here
-            const float rs = p.rscale ? __ldg(p.rscale + rw) : 1.0f;
+            // hub segment: partial (row scale applied by hub_finalize_kernel); x scaled here
+            if (PG) {
+              const float rs = p.rscale ? __ldg(p.rscale + rw) : 1.0f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xr[i] *= rs;
+              for (int i = 0; i < 8; ++i) xr[i] *= rs;
+            }
             if (outs && qvalid) store8<true, false>(p.part_acc + ((int64_t)s * p.num_hub_segs + part_slot) * D8, c, D8, dxv);
           } else if (outs && qvalid) {
             store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, dxv);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float t1 = xr[i] * a1[i];
-            d1[i] += t1;
-            d0[i] += KIND == STAG_NOISE_NORMAL ? xr[i] * a0[i] : xr[i] * a0[i] - t1;
+            if (PG) {
+              const float t1 = xr[i] * a1[i];
+              d1[i] += t1;
+              d0[i] += KIND == STAG_NOISE_NORMAL ? xr[i] * a0[i] : xr[i] * a0[i] - t1;
+            }
             a0[i] = a1[i] = 0.f;
           }
         }
@@ -628,6 +656,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
     }
   }
   cp_async_wait<0>();
+  if (!PG) return;
 
   // ---- parameter-gradient partials: groups of a warp -> warp slice -> CTA row of dp_partial -----------
   for (int o = LPR; o < 32; o <<= 1) {
@@ -1280,8 +1309,41 @@ static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t sm
   }
 }
 
+// forward (or dX-only) launches of the two-sum / per-edge-weight streaming kernel
+template <int KIND, int BODY>
+static int launch_stream2(const AggParams& p, cudaStream_t stream) {
+  const int RPW = 32 >> p.lpr_log2;
+  const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S;
+  const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
+  const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * 2 ? ctas : num_sms() * 2));
+  const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * 128 * sizeof(float4);
+  if (p.E > 0) {
+    edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
+        p, const_cast<int4*>(p.rec), 1);
+    STAG_LAUNCH_CHECK();
+  }
+  zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
+  STAG_LAUNCH_CHECK();
+  STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<KIND, BODY, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+  agg_stream_grads_kernel<KIND, BODY, false><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+  STAG_LAUNCH_CHECK();
+  return STAG_OK;
+}
+
 template <bool GRADS>
 static int launch_agg(const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
+  // streaming variants (single channel chunk, 128-bit rows, 32-bit row offsets, no in-norm)
+  const bool stream2 = !GRADS && vec && p.items && p.erow && p.eidf && p.rec && !p.in_norm && p.ncb == 1 &&
+                       p.dpad <= 256 && p.ncols * p.ldx < (1ll << 31);
+  if (stream2) {
+    if (p.kind == STAG_NOISE_NONE || (p.K == 1 && (p.kind == STAG_NOISE_EXTERNAL || p.pshape == STAG_PARAM_SCALAR)))
+      return launch_stream2<0, 1>(p, stream);
+    if (p.K != 1 && p.pshape <= STAG_PARAM_CHANNEL && (p.pshape == STAG_PARAM_CHANNEL || p.relu)) {
+      if (p.kind == STAG_NOISE_NORMAL) return launch_stream2<STAG_NOISE_NORMAL, 0>(p, stream);
+      if (p.kind == STAG_NOISE_UNIFORM) return launch_stream2<STAG_NOISE_UNIFORM, 0>(p, stream);
+    }
+  }
   if (p.kind == STAG_NOISE_NONE || p.K == 1) return launch_vec<0, 0, 0, GRADS>(p, vec, grid, smem, stream);
   if (p.kind == STAG_NOISE_EXTERNAL) return launch_vec<1, 0, 0, GRADS>(p, vec, grid, smem, stream);
   // generated per-channel noise: scalar / per-edge parameters travel with the edge record (PSH 0),
@@ -1519,13 +1581,13 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
       STAG_LAUNCH_CHECK();
     }
     if (noise->kind == STAG_NOISE_NORMAL) {
-      STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<STAG_NOISE_NORMAL>,
+      STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<STAG_NOISE_NORMAL, 0, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-      agg_stream_grads_kernel<STAG_NOISE_NORMAL><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+      agg_stream_grads_kernel<STAG_NOISE_NORMAL, 0, true><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
     } else {
-      STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<STAG_NOISE_UNIFORM>,
+      STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<STAG_NOISE_UNIFORM, 0, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-      agg_stream_grads_kernel<STAG_NOISE_UNIFORM><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+      agg_stream_grads_kernel<STAG_NOISE_UNIFORM, 0, true><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
     }
     STAG_LAUNCH_CHECK();
   } else {
