@@ -189,7 +189,11 @@ __device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t 
 #define STAG_STREAM_U 2
 #endif
 constexpr int RING_STAGES = STAG_RING_STAGES;
-constexpr int STREAM_U = STAG_STREAM_U;  // edges per ring stage, computed as independent chains
+constexpr int STREAM_U = STAG_STREAM_U;
+// next ring stage (a mask when the stage count is a power of two)
+__device__ __forceinline__ int ring_next(int i) {
+  return (RING_STAGES & (RING_STAGES - 1)) == 0 ? ((i + 1) & (RING_STAGES - 1)) : (i + 1 == RING_STAGES ? 0 : i + 1);
+}  // edges per ring stage, computed as independent chains
 
 // 16-byte async copy global -> shared; `ignore` set: the source is not read and zeros are written
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool ignore) {
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
         int fill = RING_STAGES - 1;  // ring stage filled by this iteration
         for (int i = 0; i < nstages; ++i) {
           if (i + RING_STAGES - 1 < nstages) issue_stage(i + RING_STAGES - 1, fill);
-          fill = fill + 1 == RING_STAGES ? 0 : fill + 1;
+          fill = ring_next(fill);
           cp_async_commit();
           // weights of the stage's edges (independent Philox / Box-Muller chains), gather scale folded in
           int ef[STREAM_U];
@@ -422,15 +426,16 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
               acc[5] = fmaf(w[k][5], xb.y, acc[5]);
               acc[6] = fmaf(w[k][6], xb.z, acc[6]);
               acc[7] = fmaf(w[k][7], xb.w, acc[7]);
-              if (ef[k] < 0 && part_slot < 0 && t < mylen) {  // last edge of its row: write it (group-uniform)
+              const bool row_done = ef[k] < 0 && part_slot < 0 && t < mylen;  // last edge of its row
+              if (row_done) {  // group-uniform: write the row
                 const int rw = __shfl_sync(gmask, my_row, t, LPR);
                 if (qvalid) store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, acc);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
               }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = row_done ? 0.f : acc[j];  // selects, not a merge of two copies
             }
           }
-          st = st + 1 == RING_STAGES ? 0 : st + 1;
+          st = ring_next(st);
         }
       }
       if (part_slot >= 0 && qvalid) {  // hub segment: its partial sum, combined by hub_finalize_kernel
@@ -563,8 +568,8 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
 
       auto issue = [&](int t, int slot) {
         const uint32_t u = (uint32_t)__shfl_sync(0xffffffffu, my_idx, t, LPR);
-        const int eft = __shfl_sync(0xffffffffu, my_ef, t, LPR);
-        const uint32_t rw = (uint32_t)__shfl_sync(0xffffffffu, my_row, t, LPR);
+        const int eft = PG ? __shfl_sync(0xffffffffu, my_ef, t, LPR) : 0;
+        const uint32_t rw = PG ? (uint32_t)__shfl_sync(0xffffffffu, my_row, t, LPR) : 0u;
         const float* src = gs_ + u * ldx32;
         const uint32_t dst = ring_s + (uint32_t)slot * (128u * 16u);
         const bool off_row = t >= mylen;
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
       int st = 0, fill = RING_STAGES - 1;
       for (int t = 0; t < cnt; ++t) {
         if (t + RING_STAGES - 1 < cnt) issue(t + RING_STAGES - 1, fill);
-        fill = fill + 1 == RING_STAGES ? 0 : fill + 1;
+        fill = ring_next(fill);
         cp_async_commit();
         const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
         const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
@@ -641,17 +646,24 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
           } else if (outs && qvalid) {
             store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, dxv);
           }
+          if (PG) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (PG) {
+            for (int i = 0; i < 8; ++i) {
               const float t1 = xr[i] * a1[i];
               d1[i] += t1;
               d0[i] += KIND == STAG_NOISE_NORMAL ? xr[i] * a0[i] : xr[i] * a0[i] - t1;
             }
-            a0[i] = a1[i] = 0.f;
           }
         }
-        st = st + 1 == RING_STAGES ? 0 : st + 1;
+        {
+          const bool row_done = ef < 0 && t < mylen;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // selects, not a merge of two register copies
+            a0[i] = row_done ? 0.f : a0[i];
+            if (BODY == 0) a1[i] = row_done ? 0.f : a1[i];
+          }
+        }
+        st = ring_next(st);
       }
     }
   }

@@ -1,3 +1,2 @@
-timeout 600 python -m pytest tests -m gpu -q > gpurun_out/test20.log 2>&1; echo "pytest exit $?" >> gpurun_out/test20.log
-timeout 300 python tools/bench_modes.py > gpurun_out/modes20.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_fullsize.py -m gpu -q > gpurun_out/test23.log 2>&1; echo "pytest exit $?" >> gpurun_out/test23.log
 echo done
