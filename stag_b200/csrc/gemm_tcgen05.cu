@@ -151,13 +151,33 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
   for (int kb = 0; kb < nkb; ++kb) {
     const int k0 = kb * GK;
     // ---- A tile: 128 rows x 8 chunks; W^T tile: npad rows x 8 chunks -----------------------------
-    for (int i = tid; i < GM * 8; i += GTHREADS) {
-      const int r = i >> 3, ch = i & 7;
-      put_split(a_hi, a_lo, r, ch, load_row4(p.a, p.lda, m0 + r, p.M, k0 + ch * 4, p.K, vec_a));
+    // all loads of a tile are issued before the first one is consumed (8 independent 128-bit loads in
+    // flight per thread)
+    {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = tid + j * GTHREADS;
+        v[j] = load_row4(p.a, p.lda, m0 + (i >> 3), p.M, k0 + (i & 7) * 4, p.K, vec_a);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = tid + j * GTHREADS;
+        put_split(a_hi, a_lo, i >> 3, i & 7, v[j]);
+      }
     }
-    for (int i = tid; i < p.npad * 8; i += GTHREADS) {
-      const int r = i >> 3, ch = i & 7;
-      put_split(w_hi, w_lo, r, ch, load_row4(p.wt, p.ldw, r, p.Nout, k0 + ch * 4, p.K, vec_w));
+    for (int i0 = 0; i0 < p.npad * 8; i0 += 8 * GTHREADS) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + tid + j * GTHREADS;
+        v[j] = load_row4(p.wt, p.ldw, i < p.npad * 8 ? (i >> 3) : p.Nout, p.Nout, k0 + (i & 7) * 4, p.K, vec_w);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + tid + j * GTHREADS;
+        if (i < p.npad * 8) put_split(w_hi, w_lo, i >> 3, i & 7, v[j]);
+      }
     }
     // generic-proxy writes -> visible to the tensor core's async proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

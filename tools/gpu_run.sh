@@ -1,2 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_fullsize.py -m gpu -q > gpurun_out/test23.log 2>&1; echo "pytest exit $?" >> gpurun_out/test23.log
+timeout 300 python -m pytest tests/test_gpu_gemm.py -m gpu -q > gpurun_out/test25.log 2>&1; echo "pytest exit $?" >> gpurun_out/test25.log
+timeout 300 python tools/bench_gemm.py > gpurun_out/gemm25.log 2>&1
 echo done
