@@ -1,3 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_gemm.py -m gpu -q > gpurun_out/test25.log 2>&1; echo "pytest exit $?" >> gpurun_out/test25.log
-timeout 300 python tools/bench_gemm.py > gpurun_out/gemm25.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_configs.py -m gpu -q > gpurun_out/test26.log 2>&1; echo "pytest exit $?" >> gpurun_out/test26.log
 echo done
