@@ -447,6 +447,177 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
   cp_async_wait<0>();
 }
 
+// ---- hot kernel, 16 channels per lane ----------------------------------------------------------------
+// Same stream as agg_stream_kernel for rows made of whole 128-channel groups (D = 128, 256, ...): a lane
+// owns TWO Philox blocks of an edge (quads at c, c+32, c+64, c+96 with c = 128*(sl/8) + 4*(sl%8); the 8
+// lanes of a group still read four contiguous 128-byte lines), so the per-edge bookkeeping -- record
+// broadcast, ring management, row-end test -- is paid once per 16 channels and the two blocks give two
+// independent Philox / Box-Muller chains.
+template <int KIND>
+__global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggParams p) {
+  extern __shared__ float4 ring[];  // [AGG_WARPS][RING2_STAGES][4][32]
+  constexpr int RS = 6;             // ring stages = edges in flight + 1
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int LPR = 1 << p.lpr_log2;  // lanes per row = blocks per chunk / 2
+  const int RPW = 32 >> p.lpr_log2;
+  const int sub = lane >> p.lpr_log2;
+  const int sl = lane & (LPR - 1);
+  const int D8 = p.dpad;
+  const uint32_t gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const float4* my_ring = ring + (size_t)warp * RS * 128 + lane;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
+
+  const int n_items = p.num_hub_segs + p.num_items;
+  const int IG = (n_items + RPW - 1) / RPW;
+  const int64_t total = (int64_t)IG * p.S * p.ncb;
+  const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+
+  for (int64_t item = (int64_t)blockIdx.x * AGG_WARPS + warp; item < total; item += total_warps) {
+    const int64_t outer = item / IG;
+    const int gi = (int)(item - outer * IG) * RPW + sub;
+    int s, cb;
+    if (p.cb_major) {
+      cb = (int)(outer / p.S);
+      s = (int)(outer - (int64_t)cb * p.S);
+    } else {
+      s = (int)(outer / p.ncb);
+      cb = (int)(outer - (int64_t)s * p.ncb);
+    }
+    const int c_begin = cb * p.cw;
+    const int c_end = min(c_begin + p.cw, D8);
+    int e0 = 0, e1 = 0, part_slot = -1;
+    if (gi < p.num_hub_segs) {
+      int lo = 0, hi = p.num_hubs;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.hub_seg_ptr + mid) <= gi) lo = mid; else hi = mid;
+      }
+      const int row = __ldg(p.hub_rows + lo);
+      const int k = gi - __ldg(p.hub_seg_ptr + lo);
+      e0 = __ldg(p.indptr + row) + k * kHubSegment;
+      e1 = min(e0 + kHubSegment, __ldg(p.indptr + row + 1));
+      part_slot = gi;
+    } else if (gi < n_items) {
+      const int4 it = __ldg(reinterpret_cast<const int4*>(p.items) + (gi - p.num_hub_segs));
+      e0 = it.z;
+      e1 = it.w >= 0 ? it.w : it.z;
+    }
+    const int nedges = e1 - e0;
+    int maxn = nedges;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
+
+    const float* xs = p.x + (int64_t)s * p.x_ss;
+    float* outs = p.out + (int64_t)s * p.out_ss;
+    const uint32_t smp = (uint32_t)(p.sample_base + s);
+    const uint32_t ldx32 = (uint32_t)p.ldx;
+
+    for (int c0 = c_begin; c0 < c_end; c0 += max(LPR * 16, 128)) {
+      const int c = c0 + ((sl >> 3) << 7) + ((sl & 7) << 2);
+      bool qv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qv[j] = c + 32 * j < p.D && c + 32 * j < c_end;
+      const uint32_t blk0 = (uint32_t)((c0 >> 3) + ((sl >> 3) << 4) + (sl & 7));  // Philox blocks blk0, blk0 + 8
+      const float* xc = xs + (qv[0] ? c : 0);
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+
+      auto load_records = [&](int off, int4& rc, int& rw) {
+        rc = make_int4(0, 0, 0, 0);
+        rw = 0;
+        if (off + sl < nedges) {
+          rc = __ldg(p.rec + e0 + off + sl);
+          rw = __ldg(p.erow + e0 + off + sl);
+        }
+      };
+      auto put_row = [&](float* rowp, int width) {  // the lane's four quads of one row
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + 32 * j < width && qv[j])
+            __stcs(reinterpret_cast<float4*>(rowp + c + 32 * j),
+                   make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+      };
+
+      int4 nx_rec;
+      int nx_row;
+      load_records(0, nx_rec, nx_row);
+      for (int off = 0; off < maxn; off += LPR) {
+        const int my_idx = nx_rec.x, my_ef = nx_rec.y, my_row = nx_row;
+        const float my_a = __int_as_float(nx_rec.z), my_b = __int_as_float(nx_rec.w);
+        load_records(off + LPR, nx_rec, nx_row);
+        const int cnt = min(LPR, maxn - off);
+        const int mylen = nedges - off;
+
+        auto issue = [&](int t, int slot) {
+          const uint32_t u = (uint32_t)__shfl_sync(0xffffffffu, my_idx, t, LPR);
+          const float* src = xc + u * ldx32;
+          const uint32_t dst = ring_s + (uint32_t)slot * (128u * 16u);
+          const bool off_row = t >= mylen;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cp_async16(dst + (uint32_t)j * (32u * 16u), src + 32 * j, off_row || !qv[j]);
+        };
+#pragma unroll
+        for (int i = 0; i < RS - 1; ++i) {
+          if (i < cnt) issue(i, i);
+          cp_async_commit();
+        }
+        int st = 0, fill = RS - 1;
+        for (int t = 0; t < cnt; ++t) {
+          if (t + RS - 1 < cnt) issue(t + RS - 1, fill);
+          fill = fill + 1 == RS ? 0 : fill + 1;
+          cp_async_commit();
+          const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
+          const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
+          const float B = __shfl_sync(0xffffffffu, my_b, t, LPR);
+          float w[16];
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk0 + 8u * b, smp, p.key.c3, p);
+            const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (KIND == STAG_NOISE_NORMAL) {
+                float rad, cs, sn;
+                bm_parts(q[j], rad, cs, sn);
+                const float rb = rad * B;
+                w[8 * b + 2 * j] = fmaf(cs, rb, A);
+                w[8 * b + 2 * j + 1] = fmaf(sn, rb, A);
+              } else if (KIND == STAG_NOISE_UNIFORM) {
+                w[8 * b + 2 * j] = fmaf(half_uniform<false>(q[j]), B, A);
+                w[8 * b + 2 * j + 1] = fmaf(half_uniform<true>(q[j]), B, A);
+              } else {
+                w[8 * b + 2 * j] = half_uniform<false>(q[j]) < A ? B : 0.f;
+                w[8 * b + 2 * j + 1] = half_uniform<true>(q[j]) < A ? B : 0.f;
+              }
+            }
+          }
+          cp_async_wait<RS - 1>();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 x4 = my_ring[st * 128 + j * 32];
+            acc[4 * j + 0] = fmaf(w[4 * j + 0], x4.x, acc[4 * j + 0]);
+            acc[4 * j + 1] = fmaf(w[4 * j + 1], x4.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(w[4 * j + 2], x4.z, acc[4 * j + 2]);
+            acc[4 * j + 3] = fmaf(w[4 * j + 3], x4.w, acc[4 * j + 3]);
+          }
+          const bool row_done = ef < 0 && part_slot < 0 && t < mylen;
+          if (row_done) {
+            const int rw = __shfl_sync(gmask, my_row, t, LPR);
+            put_row(outs + (int64_t)rw * p.ldo, p.D);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = row_done ? 0.f : acc[j];
+          st = st + 1 == RS ? 0 : st + 1;
+        }
+      }
+      if (part_slot >= 0) put_row(p.part_acc + ((int64_t)s * p.num_hub_segs + part_slot) * D8, D8);
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // ---- streaming gradient kernel ---------------------------------------------------------------------
 // Transposed pass with noise-parameter gradients (vi = True) for generated per-channel Normal / Uniform
 // noise with scalar or per-channel parameters (the r1 / rc posteriors), D <= 256, no in-norm.  Rows are
@@ -1294,6 +1465,29 @@ template <int KIND, bool GRADS>
 static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
   if (!GRADS && psh == 0 && !p.relu && !p.in_norm) {
     // streaming hot kernel: 128-bit rows, row offsets of the gathered operand fit 32 bits
+    static const bool wide_off = getenv("STAG_NO_WIDE") != nullptr;  // tuning knob
+    if (vec && p.items && p.erow && p.eidf && p.ncols * p.ldx < (1ll << 31) && p.dpad % 128 == 0 &&
+        p.cw % 128 == 0 && !wide_off) {
+      // 16 channels per lane: lanes per row = half the blocks of a chunk
+      AggParams q = p;
+      q.lpr_log2 = lpr_log2_for((blocks_for(p.D < p.cw ? p.D : p.cw) + 1) / 2);
+      const size_t ring_bytes = (size_t)AGG_WARPS * 6 * 128 * sizeof(float4);
+      STAG_CUDA(cudaFuncSetAttribute(agg_stream2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ring_bytes));
+      const int RPW = 32 >> q.lpr_log2;
+      const int64_t warp_items = (int64_t)((q.num_hub_segs + q.num_items + RPW - 1) / RPW) * q.S * q.ncb;
+      const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
+      const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * 2 ? ctas : num_sms() * 2));
+      if (q.E > 0) {
+        edge_record_kernel<KIND><<<(unsigned)((q.E + 255) / 256), 256, 0, stream>>>(q, const_cast<int4*>(q.rec), 0);
+        STAG_LAUNCH_CHECK();
+      }
+      zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(q);
+      STAG_LAUNCH_CHECK();
+      agg_stream2_kernel<KIND><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(q);
+      STAG_LAUNCH_CHECK();
+      return STAG_OK;
+    }
     if (vec && p.items && p.erow && p.eidf && p.ncols * p.ldx < (1ll << 31)) {
       const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * STREAM_U * 64 * sizeof(float4);
       STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
