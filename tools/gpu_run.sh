@@ -1,4 +1,6 @@
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/test27.log 2>&1; echo "pytest exit $?" >> gpurun_out/test27.log
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench27.log 2>&1
-STAG_NO_WIDE=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench27_nowide.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain28.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu28a.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain28b.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:agg_stream -s 18 -c 3 -o gpurun_out/r01_agg_stream python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu28b.log 2>&1
+timeout 300 python tools/bench_modes.py > gpurun_out/modes28.log 2>&1
 echo done
