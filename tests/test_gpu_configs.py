@@ -172,3 +172,42 @@ def test_c5_products_shaped_properties():
     lo = sb.ops.stochastic_aggregate(lg, x.detach(), spec(lg.number_of_edges()), n_samples=1)[0]
     full = sb.ops.stochastic_aggregate(g, x.detach(), spec(E), n_samples=1)[0]
     assert torch.equal(lo[part.lo:part.hi], full[part.lo:part.hi])
+
+
+def test_c2_arxiv_shaped_training_step():
+    """The BASELINE configuration itself as a program: 3-layer stag GCN 128 -> 128 -> 128 -> 40 with
+    BatchNorm / ReLU / Dropout feature layers (scripts/arxiv_mle/gcn/run.py:76-131), Normal(1, 0.4) edge noise,
+    16 MC samples batched through every layer, loss.backward(), Adam step; then MC inference."""
+    import bench
+    import stag_b200 as stag
+    src, dst = bench.synth_graph()
+    N = bench.N_NODES
+    g = stag.Graph(T(src), T(dst), N).to("cuda")
+    q_a = torch.distributions.Normal(1.0, 0.4)
+    feat_layer = lambda: stag.layers.FeatOnlyLayer(torch.nn.Sequential(  # noqa: E731
+        torch.nn.BatchNorm1d(128), torch.nn.ReLU(), torch.nn.Dropout(0.5)))
+    layers = torch.nn.ModuleList([
+        stag.layers.StagLayer(stag.zoo.GCN(128, 128), q_a=q_a), feat_layer(),
+        stag.layers.StagLayer(stag.zoo.GCN(128, 128), q_a=q_a), feat_layer(),
+        stag.layers.StagLayer(stag.zoo.GCN(128, 40, activation=lambda x: torch.softmax(x, dim=-1)), q_a=q_a),
+    ]).cuda()
+    model = stag.models.StagModel(layers)
+    opt = torch.optim.Adam(layers.parameters(), 1e-2)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(N, 128, device="cuda", generator=gen)
+    y = torch.randint(0, 40, (N,), device="cuda", generator=gen)
+    mask = torch.rand(N, device="cuda", generator=gen) < 0.5
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = model.loss(g, x, y, mask=mask, n_samples=16)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    for p in layers.parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    layers.eval()
+    with torch.no_grad():
+        probs = model.forward(g, x, n_samples=16, return_parameters=True)
+    assert probs.shape == (N, 40) and torch.allclose(probs.sum(-1), torch.ones(N, device="cuda"), atol=1e-4)
