@@ -263,11 +263,18 @@ __global__ void zero_empty_rows_kernel(const AggParams p) {
     for (int s = 0; s < p.S; ++s) {
       float* o = p.out + (int64_t)s * p.out_ss + v * p.ldo;
       for (int c = lane; c < p.D; c += 32) o[c] = 0.f;
+      if (p.in_norm && p.norm_scale_out) {  // in-norm factor of a row without edges is 1
+        float* ns = p.norm_scale_out + ((int64_t)s * p.N + v) * p.K;
+        for (int c = lane; c < p.K; c += 32) ns[c] = 1.0f;
+      }
     }
   }
 }
 
-template <int KIND>
+// INNORM (Bernoulli noise only, the pairing the reference uses: scripts/arxiv_mle/gcn/run.py:70-74): the
+// number of kept in-edges per channel is counted next to the sum and the finished row is rescaled by
+// indeg / count (stag/layers.py:8-36); the factor is written to norm_scale_out for the backward.
+template <int KIND, bool INNORM = false>
 __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream_kernel(const AggParams p) {
   extern __shared__ float4 ring[];  // [AGG_WARPS][RING_STAGES * STREAM_U][2][32]
   const int lane = threadIdx.x & 31;
@@ -333,9 +340,10 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
       const bool qvalid2 = qvalid && c + 32 < p.D;
       const uint32_t oct = (uint32_t)((c0 >> 3) + sl);  // Philox block of this lane
       const float* xc = xs + (qvalid ? c : 0);
-      float acc[8];
+      float acc[8], cntw[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 8; ++i) acc[i] = cntw[i] = 0.f;
+      int row_edges = 0;  // INNORM: in-edges of the current row seen so far
 
       // edge records of one batch, fetched one batch ahead: lane sl owns stream position off + sl
       auto load_records = [&](int off, int4& rc, int& rw) {
@@ -387,6 +395,7 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
           // weights of the stage's edges (independent Philox / Box-Muller chains), gather scale folded in
           int ef[STREAM_U];
           float w[STREAM_U][8];
+          float kept[INNORM ? STREAM_U : 1][8];  // INNORM: 1 where the Bernoulli draw kept the edge
 #pragma unroll
           for (int k = 0; k < STREAM_U; ++k) {
             const int t = i * STREAM_U + k;
@@ -407,8 +416,13 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
                 w[k][2 * j] = fmaf(half_uniform<false>(q[j]), B, A);
                 w[k][2 * j + 1] = fmaf(half_uniform<true>(q[j]), B, A);
               } else {
-                w[k][2 * j] = half_uniform<false>(q[j]) < A ? B : 0.f;
-                w[k][2 * j + 1] = half_uniform<true>(q[j]) < A ? B : 0.f;
+                const bool k0 = half_uniform<false>(q[j]) < A, k1 = half_uniform<true>(q[j]) < A;
+                w[k][2 * j] = k0 ? B : 0.f;
+                w[k][2 * j + 1] = k1 ? B : 0.f;
+                if (INNORM) {
+                  kept[k][2 * j] = k0 ? 1.0f : 0.0f;
+                  kept[k][2 * j + 1] = k1 ? 1.0f : 0.0f;
+                }
               }
             }
           }
@@ -426,13 +440,32 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
               acc[5] = fmaf(w[k][5], xb.y, acc[5]);
               acc[6] = fmaf(w[k][6], xb.z, acc[6]);
               acc[7] = fmaf(w[k][7], xb.w, acc[7]);
+              if (INNORM && t < mylen) {
+                ++row_edges;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cntw[j] += kept[INNORM ? k : 0][j];
+              }
               const bool row_done = ef[k] < 0 && part_slot < 0 && t < mylen;  // last edge of its row
               if (row_done) {  // group-uniform: write the row
                 const int rw = __shfl_sync(gmask, my_row, t, LPR);
+                if (INNORM) {
+                  float sc8[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    sc8[j] = cntw[j] != 0.f ? (float)row_edges / cntw[j] : 1.0f;
+                    acc[j] *= sc8[j];
+                  }
+                  if (p.norm_scale_out && qvalid)
+                    store8<true, false>(p.norm_scale_out + ((int64_t)s * p.N + rw) * p.K, c, p.K, sc8);
+                }
                 if (qvalid) store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, acc);
               }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] = row_done ? 0.f : acc[j];  // selects, not a merge of two copies
+              for (int j = 0; j < 8; ++j) {  // selects, not a merge of two copies
+                acc[j] = row_done ? 0.f : acc[j];
+                if (INNORM) cntw[j] = row_done ? 0.f : cntw[j];
+              }
+              if (INNORM && row_done) row_edges = 0;
             }
           }
           st = ring_next(st);
@@ -441,6 +474,7 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
       if (part_slot >= 0 && qvalid) {  // hub segment: its partial sum, combined by hub_finalize_kernel
         const int64_t o = ((int64_t)s * p.num_hub_segs + part_slot) * D8;
         store8<true, false>(p.part_acc + o, c, D8, acc);
+        if (INNORM) store8<true, false>(p.part_w + o, c, D8, cntw);
       }
     }
   }
@@ -1463,6 +1497,26 @@ static int launch_vec(const AggParams& p, bool vec, int grid, size_t smem, cudaS
 
 template <int KIND, bool GRADS>
 static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
+  if (!GRADS && psh == 0 && !p.relu && p.in_norm && KIND == STAG_NOISE_BERNOULLI && vec && p.items && p.erow &&
+      p.eidf && p.ncols * p.ldx < (1ll << 31) && (p.norm_scale_out == nullptr || p.K == p.D)) {
+    const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * STREAM_U * 64 * sizeof(float4);
+    STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<STAG_NOISE_BERNOULLI, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+    const int RPW = 32 >> p.lpr_log2;
+    const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S * p.ncb;
+    const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
+    const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * STAG_STREAM_MINBLOCKS ? ctas : num_sms() * STAG_STREAM_MINBLOCKS));
+    if (p.E > 0) {
+      edge_record_kernel<STAG_NOISE_BERNOULLI><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
+          p, const_cast<int4*>(p.rec), 0);
+      STAG_LAUNCH_CHECK();
+    }
+    zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
+    STAG_LAUNCH_CHECK();
+    agg_stream_kernel<STAG_NOISE_BERNOULLI, true><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+    STAG_LAUNCH_CHECK();
+    return STAG_OK;
+  }
   if (!GRADS && psh == 0 && !p.relu && !p.in_norm) {
     // streaming hot kernel: 128-bit rows, row offsets of the gathered operand fit 32 bits
     static const bool wide_off = getenv("STAG_NO_WIDE") != nullptr;  // tuning knob
