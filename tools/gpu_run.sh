@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/test30.log 2>&1; echo "pytest exit $?" >> gpurun_out/test30.log
-timeout 300 python tools/bench_modes.py > gpurun_out/modes30.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_spmm.py -m gpu -q -k host_buffer > gpurun_out/test31.log 2>&1; echo "pytest exit $?" >> gpurun_out/test31.log
 echo done
