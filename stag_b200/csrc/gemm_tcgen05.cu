@@ -148,25 +148,32 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
 
   const int nkb = (p.K + GK - 1) / GK;
   uint32_t phase = 0;
+  // register staging of the NEXT K block: its global loads are in flight while the tensor core works on
+  // the current one (A: 8 x 128-bit per thread; W^T: the first 128 rows, wider tiles load the rest late)
+  float4 va[8], vw[8];
+  auto load_tiles = [&](int kb) {
+    const int k0 = kb * GK;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = tid + j * GTHREADS;
+      va[j] = load_row4(p.a, p.lda, m0 + (i >> 3), p.M, k0 + (i & 7) * 4, p.K, vec_a);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = tid + j * GTHREADS;
+      vw[j] = load_row4(p.wt, p.ldw, i < p.npad * 8 ? (i >> 3) : p.Nout, p.Nout, k0 + (i & 7) * 4, p.K, vec_w);
+    }
+  };
+  load_tiles(0);
   for (int kb = 0; kb < nkb; ++kb) {
     const int k0 = kb * GK;
-    // ---- A tile: 128 rows x 8 chunks; W^T tile: npad rows x 8 chunks -----------------------------
-    // all loads of a tile are issued before the first one is consumed (8 independent 128-bit loads in
-    // flight per thread)
-    {
-      float4 v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = tid + j * GTHREADS;
-        v[j] = load_row4(p.a, p.lda, m0 + (i >> 3), p.M, k0 + (i & 7) * 4, p.K, vec_a);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = tid + j * GTHREADS;
-        put_split(a_hi, a_lo, i >> 3, i & 7, v[j]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int i = tid + j * GTHREADS;
+      put_split(a_hi, a_lo, i >> 3, i & 7, va[j]);
+      if (i < p.npad * 8) put_split(w_hi, w_lo, i >> 3, i & 7, vw[j]);
     }
-    for (int i0 = 0; i0 < p.npad * 8; i0 += 8 * GTHREADS) {
+    for (int i0 = 8 * GTHREADS; i0 < p.npad * 8; i0 += 8 * GTHREADS) {  // W^T rows 128.. (Nout > 128)
       float4 v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -198,6 +205,7 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
                        smem_u32(&mma_bar))
                    : "memory");
     }
+    if (kb + 1 < nkb) load_tiles(kb + 1);
     // the shared tiles may be overwritten (and, after the last block, TMEM read) once the MMAs are done
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
@@ -205,6 +213,9 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- epilogue: warp w owns TMEM lanes (= tile rows) 32w .. 32w+31 -------------------------------------
+  // TMEM gives a thread one row x 32 columns; a per-warp shared scratch (pitch 33) transposes that so
+  // that every store instruction writes four full 128-byte row segments
+  float* scratch = a_hi + warp * (32 * 33);  // the operand tiles are free now
   const int64_t row = m0 + warp * 32 + lane;
   const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.0f;
   for (int n0 = 0; n0 < p.npad; n0 += 32) {
@@ -221,22 +232,30 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (row < p.M) {
-      float* o = p.out + row * p.ldo + n0;
-      float y[32];
+    __syncwarp();  // the previous chunk's readers are done with the scratch
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        y[j] = __uint_as_float(v[j]) * rs;
-        if (p.bias && n0 + j < p.Nout) y[j] += __ldg(p.bias + n0 + j);
-        if (p.act == 1) y[j] = fmaxf(y[j], 0.f);
-      }
-      if (vec_o && n0 + 32 <= p.Nout) {
+    for (int j = 0; j < 32; ++j) {
+      float y = __uint_as_float(v[j]) * rs;
+      if (p.bias && n0 + j < p.Nout) y += __ldg(p.bias + n0 + j);
+      if (p.act == 1) y = fmaxf(y, 0.f);
+      scratch[lane * 33 + j] = y;
+    }
+    __syncwarp();
+    const int cq = (lane & 7) * 4;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-      } else {
+    for (int r = 0; r < 32; r += 4) {
+      const int rr = r + (lane >> 3);
+      const int64_t grow = m0 + warp * 32 + rr;
+      if (grow < p.M) {
+        const float* sp = scratch + rr * 33 + cq;
+        float* o = p.out + grow * p.ldo + n0 + cq;
+        if (vec_o && n0 + cq + 3 < p.Nout) {
+          *reinterpret_cast<float4*>(o) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < p.Nout) o[j] = y[j];
+          for (int j = 0; j < 4; ++j)
+            if (n0 + cq + j < p.Nout) o[j] = sp[j];
+        }
       }
     }
   }
