@@ -1,8 +1,11 @@
-"""Graph-convolution layers with the reference's constructors (stag/zoo/__init__.py:1-5)."""
-from .gcn import GCN
-from .graph_sage import GraphSAGE
-from .gat import GAT
-from .gin import GIN
-from .gated_gcn import GatedGCN
+"""Graph-convolution layers with the constructors of the reference's ``stag.zoo``
+(stag/zoo/__init__.py:1-5), all running their neighbour aggregation on the fused CUDA kernels."""
+from . import gat, gated_gcn, gcn, gin, graph_sage
+
+GCN = gcn.GCN
+GraphSAGE = graph_sage.GraphSAGE
+GAT = gat.GAT
+GIN = gin.GIN
+GatedGCN = gated_gcn.GatedGCN
 
 __all__ = ["GCN", "GraphSAGE", "GAT", "GIN", "GatedGCN"]
