@@ -195,3 +195,28 @@ def test_mc_forward_mean_and_determinism():
     assert torch.allclose(a.sum(-1), torch.ones_like(a.sum(-1)), atol=1e-5)
     yhat = model.forward(g, feat, n_samples=2)
     assert yhat.shape == (int(d["num_nodes"]),)
+
+
+def test_kl_fallback_with_mixture_prior():
+    """No analytic KL(Normal || MixtureSameFamily) is registered: the reference falls back to
+    log q(w) - log p(w) on the stored sample (stag/layers.py:141-143,
+    scripts/citation_rec_contrastive/gcn/run.py:44-52).  Here the sample is materialised from the same
+    Philox stream the fused forward consumed."""
+    import stag_b200 as stag
+    D = 12
+    mix = torch.distributions.MixtureSameFamily(
+        torch.distributions.Categorical(torch.tensor([0.5, 0.5]).cuda()),
+        torch.distributions.Normal(torch.tensor([0.0, 1.0]).cuda(), torch.tensor([0.3, 0.3]).cuda()))
+    q = torch.distributions.Normal(torch.ones(D), 0.2 * torch.ones(D))
+    layer = stag.layers.StagLayer(stag.zoo.GCN(D, 4), q_a=q, p_a=mix, vi=True).cuda()
+    g = stag.rand_graph(40, 300).to("cuda")
+    x = torch.randn(40, D).cuda()
+    out = layer(g, x)
+    kl = layer.kl_divergence()
+    w = layer._edge_weight_sample
+    assert w.shape == (300, D)
+    want = layer.q_a.log_prob(w).sum(-1).mean() - mix.log_prob(w).sum(-1).mean()
+    assert rel(kl, want) < 1e-6
+    assert rel(out, layer.base_layer(g, x, edge_weight=w)) < 1e-5      # the sample IS the one the kernel used
+    (out.sum() + kl).backward()
+    assert layer.q_a.loc.grad is not None and torch.isfinite(layer.q_a.log_scale.grad).all()
