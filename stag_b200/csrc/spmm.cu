@@ -487,10 +487,16 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
 // lanes of a group still read four contiguous 128-byte lines), so the per-edge bookkeeping -- record
 // broadcast, ring management, row-end test -- is paid once per 16 channels and the two blocks give two
 // independent Philox / Box-Muller chains.
-template <int KIND>
+// L = lanes per 128-channel group (8: 16 channels = 2 Philox blocks per lane, 4: 32 channels = 4 blocks
+// per lane).  Lane sl of a group owns the quads at c + 4*L*j, j < 32/L, so that the L lanes read 16*L
+// contiguous bytes (whole 32-byte sectors) per load instruction; those quads are exactly the two halves
+// of the blocks 8g + sl + L*m (g < 2, m < 8/L) of the channel map in noise.cuh.
+template <int KIND, int L>
 __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggParams p) {
-  extern __shared__ float4 ring[];  // [AGG_WARPS][RING2_STAGES][4][32]
+  extern __shared__ float4 ring[];  // [AGG_WARPS][RS][2*NB][32]
   constexpr int RS = 6;             // ring stages = edges in flight + 1
+  constexpr int NQ = 32 / L;        // quads (128-bit loads) per lane per edge
+  constexpr int NBG = 8 / L;        // blocks per lane per 64-channel half group
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int LPR = 1 << p.lpr_log2;  // lanes per row = blocks per chunk / 2
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggPa
   const int sl = lane & (LPR - 1);
   const int D8 = p.dpad;
   const uint32_t gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-  const float4* my_ring = ring + (size_t)warp * RS * 128 + lane;
+  const float4* my_ring = ring + (size_t)warp * RS * (NQ * 32) + lane;
   const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
 
   const int n_items = p.num_hub_segs + p.num_items;
@@ -547,16 +553,16 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggPa
     const uint32_t smp = (uint32_t)(p.sample_base + s);
     const uint32_t ldx32 = (uint32_t)p.ldx;
 
-    for (int c0 = c_begin; c0 < c_end; c0 += max(LPR * 16, 128)) {
-      const int c = c0 + ((sl >> 3) << 7) + ((sl & 7) << 2);
-      bool qv[4];
+    for (int c0 = c_begin; c0 < c_end; c0 += max(LPR / L, 1) * 128) {
+      const int c = c0 + (sl / L) * 128 + ((sl % L) << 2);
+      bool qv[NQ];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) qv[j] = c + 32 * j < p.D && c + 32 * j < c_end;
-      const uint32_t blk0 = (uint32_t)((c0 >> 3) + ((sl >> 3) << 4) + (sl & 7));  // Philox blocks blk0, blk0 + 8
+      for (int j = 0; j < NQ; ++j) qv[j] = c + 4 * L * j < p.D && c + 4 * L * j < c_end;
+      const uint32_t blk0 = (uint32_t)((c0 >> 3) + (sl / L) * 16 + (sl % L));  // blocks blk0 + 8g + L*m
       const float* xc = xs + (qv[0] ? c : 0);
-      float acc[16];
+      float acc[4 * NQ];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 4 * NQ; ++i) acc[i] = 0.f;
 
       auto load_records = [&](int off, int4& rc, int& rw) {
         rc = make_int4(0, 0, 0, 0);
@@ -568,9 +574,9 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggPa
       };
       auto put_row = [&](float* rowp, int width) {  // the lane's four quads of one row
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c + 32 * j < width && qv[j])
-            __stcs(reinterpret_cast<float4*>(rowp + c + 32 * j),
+        for (int j = 0; j < NQ; ++j)
+          if (c + 4 * L * j < width && qv[j])
+            __stcs(reinterpret_cast<float4*>(rowp + c + 4 * L * j),
                    make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
       };
 
@@ -587,10 +593,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggPa
         auto issue = [&](int t, int slot) {
           const uint32_t u = (uint32_t)__shfl_sync(0xffffffffu, my_idx, t, LPR);
           const float* src = xc + u * ldx32;
-          const uint32_t dst = ring_s + (uint32_t)slot * (128u * 16u);
+          const uint32_t dst = ring_s + (uint32_t)slot * (uint32_t)(NQ * 32 * 16);
           const bool off_row = t >= mylen;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) cp_async16(dst + (uint32_t)j * (32u * 16u), src + 32 * j, off_row || !qv[j]);
+          for (int j = 0; j < NQ; ++j) cp_async16(dst + (uint32_t)j * (32u * 16u), src + 4 * L * j, off_row || !qv[j]);
         };
 #pragma unroll
         for (int i = 0; i < RS - 1; ++i) {
@@ -605,10 +611,12 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggPa
           const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
           const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
           const float B = __shfl_sync(0xffffffffu, my_b, t, LPR);
-          float w[16];
+          cp_async_wait<RS - 1>();
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk0 + 8u * b, smp, p.key.c3, p);
+          for (int b = 0; b < 2 * NBG; ++b) {
+            const int g = b / NBG, m = b % NBG;  // 64-channel half group, block within it
+            float w[8];
+            const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk0 + (uint32_t)(8 * g + L * m), smp, p.key.c3, p);
             const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -616,25 +624,27 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggPa
                 float rad, cs, sn;
                 bm_parts(q[j], rad, cs, sn);
                 const float rb = rad * B;
-                w[8 * b + 2 * j] = fmaf(cs, rb, A);
-                w[8 * b + 2 * j + 1] = fmaf(sn, rb, A);
+                w[2 * j] = fmaf(cs, rb, A);
+                w[2 * j + 1] = fmaf(sn, rb, A);
               } else if (KIND == STAG_NOISE_UNIFORM) {
-                w[8 * b + 2 * j] = fmaf(half_uniform<false>(q[j]), B, A);
-                w[8 * b + 2 * j + 1] = fmaf(half_uniform<true>(q[j]), B, A);
+                w[2 * j] = fmaf(half_uniform<false>(q[j]), B, A);
+                w[2 * j + 1] = fmaf(half_uniform<true>(q[j]), B, A);
               } else {
-                w[8 * b + 2 * j] = half_uniform<false>(q[j]) < A ? B : 0.f;
-                w[8 * b + 2 * j + 1] = half_uniform<true>(q[j]) < A ? B : 0.f;
+                w[2 * j] = half_uniform<false>(q[j]) < A ? B : 0.f;
+                w[2 * j + 1] = half_uniform<true>(q[j]) < A ? B : 0.f;
               }
             }
-          }
-          cp_async_wait<RS - 1>();
+            // the block's slots 0..3 / 4..7 are the lane's quads j = g*(16/L) + m + h*(8/L), h = 0 / 1
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 x4 = my_ring[st * 128 + j * 32];
-            acc[4 * j + 0] = fmaf(w[4 * j + 0], x4.x, acc[4 * j + 0]);
-            acc[4 * j + 1] = fmaf(w[4 * j + 1], x4.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(w[4 * j + 2], x4.z, acc[4 * j + 2]);
-            acc[4 * j + 3] = fmaf(w[4 * j + 3], x4.w, acc[4 * j + 3]);
+            for (int h = 0; h < 2; ++h) {
+              const int j = g * (16 / L) + m + h * NBG;
+              const float4 x4 = my_ring[st * (NQ * 32) + j * 32];
+              float* a4 = acc + 4 * j;
+              a4[0] = fmaf(w[4 * h + 0], x4.x, a4[0]);
+              a4[1] = fmaf(w[4 * h + 1], x4.y, a4[1]);
+              a4[2] = fmaf(w[4 * h + 2], x4.z, a4[2]);
+              a4[3] = fmaf(w[4 * h + 3], x4.w, a4[3]);
+            }
           }
           const bool row_done = ef < 0 && part_slot < 0 && t < mylen;
           if (row_done) {
@@ -642,7 +652,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggPa
             put_row(outs + (int64_t)rw * p.ldo, p.D);
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = row_done ? 0.f : acc[j];
+          for (int j = 0; j < 4 * NQ; ++j) acc[j] = row_done ? 0.f : acc[j];
           st = st + 1 == RS ? 0 : st + 1;
         }
       }
@@ -1522,12 +1532,13 @@ static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t sm
     static const bool wide_off = getenv("STAG_NO_WIDE") != nullptr;  // tuning knob
     if (vec && p.items && p.erow && p.eidf && p.ncols * p.ldx < (1ll << 31) && p.dpad % 128 == 0 &&
         p.cw % 128 == 0 && !wide_off) {
-      // 16 channels per lane: lanes per row = half the blocks of a chunk
+      // NB Philox blocks (8 * NB channels) per lane: lanes per row = blocks of a chunk / NB
+      // L = 8 lanes per 128 channels (2 blocks per lane); L = 4 (32 channels per lane) was measured slower
+      // (2.7 vs 1.95 ms per launch at the arxiv shape: register-bound) and is not instantiated
+      const int nb = 2;
       AggParams q = p;
-      q.lpr_log2 = lpr_log2_for((blocks_for(p.D < p.cw ? p.D : p.cw) + 1) / 2);
-      const size_t ring_bytes = (size_t)AGG_WARPS * 6 * 128 * sizeof(float4);
-      STAG_CUDA(cudaFuncSetAttribute(agg_stream2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)ring_bytes));
+      q.lpr_log2 = lpr_log2_for((blocks_for(p.D < p.cw ? p.D : p.cw) + nb - 1) / nb);
+      const size_t ring_bytes = (size_t)AGG_WARPS * 6 * (2 * nb * 32) * sizeof(float4);
       const int RPW = 32 >> q.lpr_log2;
       const int64_t warp_items = (int64_t)((q.num_hub_segs + q.num_items + RPW - 1) / RPW) * q.S * q.ncb;
       const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
@@ -1538,7 +1549,9 @@ static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t sm
       }
       zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(q);
       STAG_LAUNCH_CHECK();
-      agg_stream2_kernel<KIND><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(q);
+      STAG_CUDA(cudaFuncSetAttribute(agg_stream2_kernel<KIND, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ring_bytes));
+      agg_stream2_kernel<KIND, 8><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(q);
       STAG_LAUNCH_CHECK();
       return STAG_OK;
     }
