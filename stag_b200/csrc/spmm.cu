@@ -188,6 +188,10 @@ __device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t 
 #ifndef STAG_STREAM_U
 #define STAG_STREAM_U 2
 #endif
+#ifndef STAG_RING2_STAGES
+#define STAG_RING2_STAGES 6
+#endif
+constexpr int RING2_STAGES = STAG_RING2_STAGES;  // agg_stream2_kernel
 constexpr int RING_STAGES = STAG_RING_STAGES;
 constexpr int STREAM_U = STAG_STREAM_U;
 // next ring stage (a mask when the stage count is a power of two)
@@ -494,7 +498,7 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
 template <int KIND, int L>
 __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggParams p) {
   extern __shared__ float4 ring[];  // [AGG_WARPS][RS][2*NB][32]
-  constexpr int RS = 6;             // ring stages = edges in flight + 1
+  constexpr int RS = RING2_STAGES;  // ring stages = edges in flight + 1
   constexpr int NQ = 32 / L;        // quads (128-bit loads) per lane per edge
   constexpr int NBG = 8 / L;        // blocks per lane per 64-channel half group
   const int lane = threadIdx.x & 31;
@@ -1538,7 +1542,7 @@ static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t sm
       const int nb = 2;
       AggParams q = p;
       q.lpr_log2 = lpr_log2_for((blocks_for(p.D < p.cw ? p.D : p.cw) + nb - 1) / nb);
-      const size_t ring_bytes = (size_t)AGG_WARPS * 6 * (2 * nb * 32) * sizeof(float4);
+      const size_t ring_bytes = (size_t)AGG_WARPS * RING2_STAGES * (2 * nb * 32) * sizeof(float4);
       const int RPW = 32 >> q.lpr_log2;
       const int64_t warp_items = (int64_t)((q.num_hub_segs + q.num_items + RPW - 1) / RPW) * q.S * q.ncb;
       const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
