@@ -365,7 +365,7 @@ def run_ours(args, rank, world):
     peak, peak_src = peaks()
     achieved = alg / (avg_ms * 1e-3) / 1e9
     step_bytes = bytes_fwd(S, True) + 2 * bytes_fwd(S, False) + 2 * bytes_bwd(S, vi, False) + bytes_bwd(S, vi, True)
-    roof = {"bound": "hbm", "kernel": "stag::agg_stream2_kernel<NORMAL> (%s launches)" % dom, "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": "stag::agg_stream_kernel<NORMAL, 2 blocks per lane> (%s launches)" % dom, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
             "share_of_step": tot[dom] / sum(tot.values()),

@@ -52,6 +52,7 @@ struct AggParams {
   const int4* rec;           // per-call edge records (edge_record_kernel), workspace
   int num_items;
   uint32_t rk[2 * kPhiloxRounds];  // Philox round keys
+  uint32_t kf;                     // 0x4B000000 (2^23 as float bits), read from the constant bank by PRMT
   int num_hubs, num_hub_segs;
   int N;
   int64_t ncols;  // rows of the gathered operand
@@ -165,35 +166,11 @@ __device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t 
   }
 }
 
-// ---- hot kernel ------------------------------------------------------------------------------
-// MODE 2 / PSH 0 without relu / in-norm / gradients (the arxiv_mle configuration, forward and
-// transposed): generated per-channel noise with scalar or per-edge parameters, gather scale folded
-// into the per-edge pair (A, B).
-//
-// Unit of work of a lane group: one STREAM ITEM = a range of consecutive rows holding about
-// kRangeEdges stored edges (StagGraph::items) or one hub segment.  The group walks the item's
-// edges as ONE contiguous stream: edge records (neighbour, edge id, folded parameters, row and row
-// scale) are fetched in coalesced batches of LPR one batch AHEAD of their use, the gathered rows
-// are staged through a per-lane shared-memory ring filled by cp.async (LDGSTS, RING_STAGES - 1
-// edges in flight, no registers held), and a row is written when the stream crosses into the next
-// one.  So the only latency a warp ever waits for is one ring fill per batch, every group of a
-// warp has the same trip count whatever the degree distribution, and a zero-degree row costs one
-// store.  A lane only reads ring slots it wrote itself: cp.async.wait_group orders them, no barrier.
+// ---- shared pieces of the streaming kernels -------------------------------------------------------------
 #ifndef STAG_RING_STAGES
 #define STAG_RING_STAGES 4
 #endif
-#ifndef STAG_STREAM_MINBLOCKS
-#define STAG_STREAM_MINBLOCKS 2
-#endif
-#ifndef STAG_STREAM_U
-#define STAG_STREAM_U 2
-#endif
-#ifndef STAG_RING2_STAGES
-#define STAG_RING2_STAGES 6
-#endif
-constexpr int RING2_STAGES = STAG_RING2_STAGES;  // agg_stream2_kernel
 constexpr int RING_STAGES = STAG_RING_STAGES;
-constexpr int STREAM_U = STAG_STREAM_U;
 // next ring stage (a mask when the stage count is a power of two)
 __device__ __forceinline__ int ring_next(int i) {
   return (RING_STAGES & (RING_STAGES - 1)) == 0 ? ((i + 1) & (RING_STAGES - 1)) : (i + 1 == RING_STAGES ? 0 : i + 1);
@@ -236,6 +213,8 @@ __device__ __forceinline__ uint4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2
 // store.  Hub rows keep their row scale out of (A, B): hub_finalize_kernel applies it once.
 template <int KIND>
 __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, int scales_only) {
+  // scales_only: 0 = (A, B) as documented above, 1 = the two scalings only (gradient / two-sum kernels),
+  // 2 = like 0 with sqrt(2 ln 2) folded into B of Normal noise (agg_stream3_kernel takes sqrt(-lg2 u1) as radius)
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p.E) return;
   const int idx = __ldg(p.indices + j);
@@ -243,7 +222,7 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, in
   const int row = __ldg(p.erow + j);
   float sc = p.gscale ? __ldg(p.gscale + idx) : 1.0f;
   if (p.rscale && __ldg(p.indptr + row + 1) - __ldg(p.indptr + row) <= kHubThreshold) sc *= __ldg(p.rscale + row);
-  if (scales_only) {  // gradient kernel: the parameters stay in registers, only the two scalings are folded
+  if (scales_only == 1) {  // gradient kernel: the parameters stay in registers, only the two scalings are folded
     rec[j] = make_int4(idx, ef, __float_as_int(sc), 0);
     return;
   }
@@ -251,7 +230,7 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, in
   const float pa = __ldg(p.p0 + pi);
   const float pb = KIND != STAG_NOISE_BERNOULLI ? __ldg(p.p1 + pi) : 0.f;
   float a, b;
-  if (KIND == STAG_NOISE_NORMAL) { a = sc * pa; b = sc * pb; }
+  if (KIND == STAG_NOISE_NORMAL) { a = sc * pa; b = sc * pb * (scales_only == 2 ? 1.1774100225154747f : 1.0f); }
   else if (KIND == STAG_NOISE_UNIFORM) { a = sc * pa; b = sc * (pb - pa); }
   else { a = pa; b = sc; }
   rec[j] = make_int4(idx, ef, __float_as_int(a), __float_as_int(b));
@@ -275,22 +254,84 @@ __global__ void zero_empty_rows_kernel(const AggParams p) {
   }
 }
 
-// INNORM (Bernoulli noise only, the pairing the reference uses: scripts/arxiv_mle/gcn/run.py:70-74): the
-// number of kept in-edges per channel is counted next to the sum and the finished row is rescaled by
-// indeg / count (stag/layers.py:8-36); the factor is written to norm_scale_out for the backward.
-template <int KIND, bool INNORM = false>
-__global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream_kernel(const AggParams p) {
-  extern __shared__ float4 ring[];  // [AGG_WARPS][RING_STAGES * STREAM_U][2][32]
+// ---- hot kernel -------------------------------------------------------------------------------------
+// Generated per-channel noise with scalar or per-edge parameters, no relu, no parameter gradients: the
+// arxiv_mle configuration, forward AND transposed (dX) pass.  Template switches:
+//   NB      Philox blocks (8 channels each) per lane: 2 for rows made of 128-channel groups (16 channels per
+//           lane, 8 lanes per 128 channels), 1 otherwise (8 lanes per 64 channels)
+//   FULL    every row is made of whole groups and there is one column block: no quad predicates
+//   INNORM  Bernoulli + in-norm (the pairing the reference uses, scripts/arxiv_mle/gcn/run.py:70-74): the kept
+//           in-edges per channel are counted next to the sum, the finished row is rescaled by indeg / count
+//           (stag/layers.py:8-36) and the factor is written to norm_scale_out for the backward
+//
+// Unit of work of a lane group (LPR lanes): one STREAM ITEM = consecutive rows holding about kRangeEdges stored
+// edges (StagGraph::items) or one hub segment, walked as ONE stream of edges:
+//   * the edge records {neighbour, eid | last << 31, A, B'} (edge_record_kernel: both degree scalings and the
+//     distribution parameters folded into (A, B'), w * scale = A + B' * raw) and the row of every edge reach
+//     the group through a small shared-memory ring filled by cp.async two chunks (of LPR edges) ahead and are
+//     read back with one broadcast LDS.128 (+ one LDS.32 for the neighbour of the edge being prefetched): no
+//     record registers, no shuffles, no dependent global loads;
+//   * the gathered row of edge t + RS is requested (cp.async, LDGSTS) into the ring slot edge t has just been
+//     consumed from: RS = 4 edges in flight per lane, a lane only reads data slots it wrote itself;
+//   * the loop is unrolled by RS, so every ring slot is an immediate offset;
+//   * Box-Muller with sqrt(2 ln 2) folded into B' and the 2^23 magic of the half -> float conversion read
+//     from the constant bank (AggParams::kf): a pair of normals costs PRMT, FFMA, LG2, SQRT | PRMT, FFMA,
+//     FMUL.RZ, COS, SIN | FMUL, 2 FFMA (w) + 2 FFMA (accumulate);
+//   * a row is written (st.global.cs) when the stream passes its last edge; rows without edges are cleared by
+//     zero_empty_rows_kernel; hub segments leave partial sums for hub_finalize_kernel.
+// Where the time goes (B200, arxiv shape, 16 samples): DESIGN.md section 5.
+constexpr int S3_RS = 4;    // data ring slots = edges in flight per lane
+constexpr int S3_NBUF = 4;  // record chunks (of LPR edges) in the record ring
+// per warp: [RS][2 NB quads][32 lanes] float4 data, then [groups][NBUF * LPR] int4 records and
+// [groups][NBUF * LPR] int rows; group g starts 16 (4) bytes past a multiple of 128 so that the broadcast
+// reads of the groups of a warp fall into different banks
+constexpr uint32_t S3_REC_BYTES = S3_NBUF * 32 * 16 + 128;
+constexpr uint32_t S3_ROW_BYTES = S3_NBUF * 32 * 4 + 128;
+__host__ __device__ constexpr uint32_t s3_data_bytes(int nb) { return (uint32_t)(S3_RS * 2 * nb * 32 * 16); }
+__host__ __device__ constexpr uint32_t s3_warp_bytes(int nb) { return s3_data_bytes(nb) + S3_REC_BYTES + S3_ROW_BYTES; }
+__host__ __device__ constexpr int s3_min_blocks(int nb, bool innorm) { return (nb == 1 && !innorm) ? 3 : 2; }
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src, bool ignore) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tcp.async.ca.shared.global [%0], [%1], 4, p;\n\t}" ::"r"(dst_smem),
+      "l"(src), "r"((int)ignore)
+      : "memory");
+}
+__device__ __forceinline__ int4 lds128(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+template <int KIND, int NB, bool FULL, bool INNORM>
+__global__ void __launch_bounds__(AGG_THREADS, s3_min_blocks(NB, INNORM)) agg_stream_kernel(const AggParams p) {
+  extern __shared__ float4 ring[];
+  constexpr int RS = S3_RS, NQ = 2 * NB, GW = 64 * NB, NA = 4 * NQ;
+  constexpr uint32_t DATA_BYTES = s3_data_bytes(NB), WARP_BYTES = s3_warp_bytes(NB), SLOT = NQ * 512u;
+  static_assert(!INNORM || KIND == STAG_NOISE_BERNOULLI, "in-norm is fused for Bernoulli noise only");
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int LPR = 1 << p.lpr_log2;
+  const int LPR = 1 << p.lpr_log2;  // lanes per row (>= 8); a record chunk is LPR edges
   const int RPW = 32 >> p.lpr_log2;
   const int sub = lane >> p.lpr_log2;
   const int sl = lane & (LPR - 1);
   const int D8 = p.dpad;
-  const uint32_t gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-  const float4* my_ring = ring + (size_t)warp * RING_STAGES * STREAM_U * 64 + lane;
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
+  const uint32_t warp_s = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)warp * WARP_BYTES;
+  const uint32_t data_s = warp_s + (uint32_t)lane * 16u;  // + slot * SLOT + quad * 512
+  const uint32_t rmask = (uint32_t)(S3_NBUF * LPR) - 1u;  // record ring positions of a group
+  const uint32_t rec_g = warp_s + DATA_BYTES + (uint32_t)(sub * S3_NBUF * LPR) * 16u + (uint32_t)sub * 16u;
+  const uint32_t row_g = warp_s + DATA_BYTES + S3_REC_BYTES + (uint32_t)(sub * S3_NBUF * LPR) * 4u + (uint32_t)sub * 4u;
+  const uint32_t kf = p.kf;
 
   const int n_items = p.num_hub_segs + p.num_items;
   const int IG = (n_items + RPW - 1) / RPW;  // warp items per (sample, column block)
@@ -329,6 +370,7 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
       e1 = it.w >= 0 ? it.w : it.z;  // it.w < 0: placeholder of a hub row, nothing to do here
     }
     const int nedges = e1 - e0;
+    const int rowlim = part_slot < 0 ? nedges : 0;  // edges that may close a row (none in a hub segment)
     int maxn = nedges;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
@@ -336,334 +378,158 @@ __global__ void __launch_bounds__(AGG_THREADS, STAG_STREAM_MINBLOCKS) agg_stream
     const float* xs = p.x + (int64_t)s * p.x_ss;
     float* outs = p.out + (int64_t)s * p.out_ss;
     const uint32_t smp = (uint32_t)(p.sample_base + s);
-    const uint32_t ldx32 = (uint32_t)p.ldx;
+    const uint32_t ldxb = (uint32_t)p.ldx * 4u;
+    const int4* recp = p.rec + e0;
+    const int32_t* rowp = p.erow + e0;
 
-    for (int c0 = c_begin; c0 < c_end; c0 += max(LPR * 8, 64)) {
-      const int c = first_chan(c0, sl);
-      const bool qvalid = c < p.D && c < c_end;
-      const bool qvalid2 = qvalid && c + 32 < p.D;
-      const uint32_t oct = (uint32_t)((c0 >> 3) + sl);  // Philox block of this lane
-      const float* xc = xs + (qvalid ? c : 0);
-      float acc[8], cntw[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = cntw[i] = 0.f;
-      int row_edges = 0;  // INNORM: in-edges of the current row seen so far
-
-      // edge records of one batch, fetched one batch ahead: lane sl owns stream position off + sl
-      auto load_records = [&](int off, int4& rc, int& rw) {
-        rc = make_int4(0, 0, 0, 0);
-        rw = 0;
-        if (off + sl < nedges) {
-          rc = __ldg(p.rec + e0 + off + sl);
-          rw = __ldg(p.erow + e0 + off + sl);
-        }
-      };
-
-      int4 nx_rec;
-      int nx_row;
-      load_records(0, nx_rec, nx_row);
-      for (int off = 0; off < maxn; off += LPR) {
-        const int my_idx = nx_rec.x, my_ef = nx_rec.y, my_row = nx_row;
-        const float my_a = __int_as_float(nx_rec.z), my_b = __int_as_float(nx_rec.w);
-        load_records(off + LPR, nx_rec, nx_row);
-        const int cnt = min(LPR, maxn - off);
-        const int mylen = nedges - off;  // edges this group still has in this batch (may be <= 0)
-
-        // stage i of the ring = the U consecutive edges i*U .. i*U+U-1 of this batch
-        auto issue_stage = [&](int i, int slot) {
-#pragma unroll
-          for (int k = 0; k < STREAM_U; ++k) {
-            const int t = i * STREAM_U + k;
-            if (t < cnt) {  // warp-uniform
-              const uint32_t u = (uint32_t)__shfl_sync(0xffffffffu, my_idx, t, LPR);
-              const float* src = xc + u * ldx32;  // 32-bit row offset (checked by the launcher)
-              const uint32_t dst = ring_s + (uint32_t)(slot * STREAM_U + k) * (64u * 16u);
-              const bool off_row = t >= mylen;  // beyond this group's edges: zero fill
-              cp_async16(dst, src, off_row || !qvalid);
-              cp_async16(dst + 32u * 16u, src + 32, off_row || !qvalid2);
-            }
-          }
-        };
-        const int nstages = (cnt + STREAM_U - 1) / STREAM_U;
-#pragma unroll
-        for (int i = 0; i < RING_STAGES - 1; ++i) {
-          if (i < nstages) issue_stage(i, i);
-          cp_async_commit();
-        }
-        int st = 0;                 // ring stage consumed by this iteration
-        int fill = RING_STAGES - 1;  // ring stage filled by this iteration
-        for (int i = 0; i < nstages; ++i) {
-          if (i + RING_STAGES - 1 < nstages) issue_stage(i + RING_STAGES - 1, fill);
-          fill = ring_next(fill);
-          cp_async_commit();
-          // weights of the stage's edges (independent Philox / Box-Muller chains), gather scale folded in
-          int ef[STREAM_U];
-          float w[STREAM_U][8];
-          float kept[INNORM ? STREAM_U : 1][8];  // INNORM: 1 where the Bernoulli draw kept the edge
-#pragma unroll
-          for (int k = 0; k < STREAM_U; ++k) {
-            const int t = i * STREAM_U + k;
-            ef[k] = __shfl_sync(0xffffffffu, my_ef, t, LPR);
-            const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
-            const float B = __shfl_sync(0xffffffffu, my_b, t, LPR);
-            const uint4 r4 = philox_rk((uint32_t)(ef[k] & 0x7fffffff), oct, smp, p.key.c3, p);
-            const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (KIND == STAG_NOISE_NORMAL) {
-                float rad, cs, sn;
-                bm_parts(q[j], rad, cs, sn);
-                const float rb = rad * B;
-                w[k][2 * j] = fmaf(cs, rb, A);
-                w[k][2 * j + 1] = fmaf(sn, rb, A);
-              } else if (KIND == STAG_NOISE_UNIFORM) {
-                w[k][2 * j] = fmaf(half_uniform<false>(q[j]), B, A);
-                w[k][2 * j + 1] = fmaf(half_uniform<true>(q[j]), B, A);
-              } else {
-                const bool k0 = half_uniform<false>(q[j]) < A, k1 = half_uniform<true>(q[j]) < A;
-                w[k][2 * j] = k0 ? B : 0.f;
-                w[k][2 * j + 1] = k1 ? B : 0.f;
-                if (INNORM) {
-                  kept[k][2 * j] = k0 ? 1.0f : 0.0f;
-                  kept[k][2 * j + 1] = k1 ? 1.0f : 0.0f;
-                }
-              }
-            }
-          }
-          cp_async_wait<RING_STAGES - 1>();
-#pragma unroll
-          for (int k = 0; k < STREAM_U; ++k) {
-            const int t = i * STREAM_U + k;
-            if (t < cnt) {  // warp-uniform
-              const float4 xa = my_ring[(st * STREAM_U + k) * 64], xb = my_ring[(st * STREAM_U + k) * 64 + 32];
-              acc[0] = fmaf(w[k][0], xa.x, acc[0]);
-              acc[1] = fmaf(w[k][1], xa.y, acc[1]);
-              acc[2] = fmaf(w[k][2], xa.z, acc[2]);
-              acc[3] = fmaf(w[k][3], xa.w, acc[3]);
-              acc[4] = fmaf(w[k][4], xb.x, acc[4]);
-              acc[5] = fmaf(w[k][5], xb.y, acc[5]);
-              acc[6] = fmaf(w[k][6], xb.z, acc[6]);
-              acc[7] = fmaf(w[k][7], xb.w, acc[7]);
-              if (INNORM && t < mylen) {
-                ++row_edges;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) cntw[j] += kept[INNORM ? k : 0][j];
-              }
-              const bool row_done = ef[k] < 0 && part_slot < 0 && t < mylen;  // last edge of its row
-              if (row_done) {  // group-uniform: write the row
-                const int rw = __shfl_sync(gmask, my_row, t, LPR);
-                if (INNORM) {
-                  float sc8[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    sc8[j] = cntw[j] != 0.f ? (float)row_edges / cntw[j] : 1.0f;
-                    acc[j] *= sc8[j];
-                  }
-                  if (p.norm_scale_out && qvalid)
-                    store8<true, false>(p.norm_scale_out + ((int64_t)s * p.N + rw) * p.K, c, p.K, sc8);
-                }
-                if (qvalid) store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, acc);
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {  // selects, not a merge of two copies
-                acc[j] = row_done ? 0.f : acc[j];
-                if (INNORM) cntw[j] = row_done ? 0.f : cntw[j];
-              }
-              if (INNORM && row_done) row_edges = 0;
-            }
-          }
-          st = ring_next(st);
-        }
-      }
-      if (part_slot >= 0 && qvalid) {  // hub segment: its partial sum, combined by hub_finalize_kernel
-        const int64_t o = ((int64_t)s * p.num_hub_segs + part_slot) * D8;
-        store8<true, false>(p.part_acc + o, c, D8, acc);
-        if (INNORM) store8<true, false>(p.part_w + o, c, D8, cntw);
-      }
-    }
-  }
-  cp_async_wait<0>();
-}
-
-// ---- hot kernel, 16 channels per lane ----------------------------------------------------------------
-// Same stream as agg_stream_kernel for rows made of whole 128-channel groups (D = 128, 256, ...): a lane
-// owns TWO Philox blocks of an edge (quads at c, c+32, c+64, c+96 with c = 128*(sl/8) + 4*(sl%8); the 8
-// lanes of a group still read four contiguous 128-byte lines), so the per-edge bookkeeping -- record
-// broadcast, ring management, row-end test -- is paid once per 16 channels and the two blocks give two
-// independent Philox / Box-Muller chains.
-// L = lanes per 128-channel group (8: 16 channels = 2 Philox blocks per lane, 4: 32 channels = 4 blocks
-// per lane).  Lane sl of a group owns the quads at c + 4*L*j, j < 32/L, so that the L lanes read 16*L
-// contiguous bytes (whole 32-byte sectors) per load instruction; those quads are exactly the two halves
-// of the blocks 8g + sl + L*m (g < 2, m < 8/L) of the channel map in noise.cuh.
-template <int KIND, int L>
-__global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream2_kernel(const AggParams p) {
-  extern __shared__ float4 ring[];  // [AGG_WARPS][RS][2*NB][32]
-  constexpr int RS = RING2_STAGES;  // ring stages = edges in flight + 1
-  constexpr int NQ = 32 / L;        // quads (128-bit loads) per lane per edge
-  constexpr int NBG = 8 / L;        // blocks per lane per 64-channel half group
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int LPR = 1 << p.lpr_log2;  // lanes per row = blocks per chunk / 2
-  const int RPW = 32 >> p.lpr_log2;
-  const int sub = lane >> p.lpr_log2;
-  const int sl = lane & (LPR - 1);
-  const int D8 = p.dpad;
-  const uint32_t gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-  const float4* my_ring = ring + (size_t)warp * RS * (NQ * 32) + lane;
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
-
-  const int n_items = p.num_hub_segs + p.num_items;
-  const int IG = (n_items + RPW - 1) / RPW;
-  const int64_t total = (int64_t)IG * p.S * p.ncb;
-  const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
-
-  for (int64_t item = (int64_t)blockIdx.x * AGG_WARPS + warp; item < total; item += total_warps) {
-    const int64_t outer = item / IG;
-    const int gi = (int)(item - outer * IG) * RPW + sub;
-    int s, cb;
-    if (p.cb_major) {
-      cb = (int)(outer / p.S);
-      s = (int)(outer - (int64_t)cb * p.S);
-    } else {
-      s = (int)(outer / p.ncb);
-      cb = (int)(outer - (int64_t)s * p.ncb);
-    }
-    const int c_begin = cb * p.cw;
-    const int c_end = min(c_begin + p.cw, D8);
-    int e0 = 0, e1 = 0, part_slot = -1;
-    if (gi < p.num_hub_segs) {
-      int lo = 0, hi = p.num_hubs;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(p.hub_seg_ptr + mid) <= gi) lo = mid; else hi = mid;
-      }
-      const int row = __ldg(p.hub_rows + lo);
-      const int k = gi - __ldg(p.hub_seg_ptr + lo);
-      e0 = __ldg(p.indptr + row) + k * kHubSegment;
-      e1 = min(e0 + kHubSegment, __ldg(p.indptr + row + 1));
-      part_slot = gi;
-    } else if (gi < n_items) {
-      const int4 it = __ldg(reinterpret_cast<const int4*>(p.items) + (gi - p.num_hub_segs));
-      e0 = it.z;
-      e1 = it.w >= 0 ? it.w : it.z;
-    }
-    const int nedges = e1 - e0;
-    int maxn = nedges;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
-
-    const float* xs = p.x + (int64_t)s * p.x_ss;
-    float* outs = p.out + (int64_t)s * p.out_ss;
-    const uint32_t smp = (uint32_t)(p.sample_base + s);
-    const uint32_t ldx32 = (uint32_t)p.ldx;
-
-    for (int c0 = c_begin; c0 < c_end; c0 += max(LPR / L, 1) * 128) {
-      const int c = c0 + (sl / L) * 128 + ((sl % L) << 2);
+    for (int c0 = c_begin; c0 < c_end; c0 += (LPR >> 3) * GW) {
+      const int c = c0 + (sl >> 3) * GW + ((sl & 7) << 2);  // quads at c + 32 j
       bool qv[NQ];
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) qv[j] = c + 4 * L * j < p.D && c + 4 * L * j < c_end;
-      const uint32_t blk0 = (uint32_t)((c0 >> 3) + (sl / L) * 16 + (sl % L));  // blocks blk0 + 8g + L*m
-      const float* xc = xs + (qv[0] ? c : 0);
-      float acc[4 * NQ];
+      for (int j = 0; j < NQ; ++j) qv[j] = FULL || (c + 32 * j < p.D && c + 32 * j < c_end);
+      const uint32_t blk0 = (uint32_t)((c0 >> 3) + (sl >> 3) * 8 * NB + (sl & 7));  // Philox blocks blk0 + 8 g
+      const char* xcb = reinterpret_cast<const char*>(xs + (qv[0] ? c : 0));
+      float acc[NA], cntw[INNORM ? NA : 1];
 #pragma unroll
-      for (int i = 0; i < 4 * NQ; ++i) acc[i] = 0.f;
+      for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+      if (INNORM) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) cntw[INNORM ? i : 0] = 0.f;
+      }
+      int row_edges = 0;  // INNORM: in-edges of the current row seen so far
 
-      auto load_records = [&](int off, int4& rc, int& rw) {
-        rc = make_int4(0, 0, 0, 0);
-        rw = 0;
-        if (off + sl < nedges) {
-          rc = __ldg(p.rec + e0 + off + sl);
-          rw = __ldg(p.erow + e0 + off + sl);
-        }
+      // record chunk: edges first + sl of the item -> ring position (first + sl) & rmask (zeros past the end)
+      auto fetch_chunk = [&](int first) {
+        const int e = first + sl;
+        const uint32_t pos = (uint32_t)e & rmask;
+        const bool off = e >= nedges;
+        cp_async16(rec_g + pos * 16u, recp + (off ? 0 : e), off);
+        cp_async4(row_g + pos * 4u, rowp + (off ? 0 : e), off);
       };
-      auto put_row = [&](float* rowp, int width) {  // the lane's four quads of one row
+      // gathered row of edge e (its neighbour read from the record ring) -> data ring slot
+      auto issue = [&](int e, uint32_t rec_addr, int slot) {
+        const uint32_t u = (uint32_t)lds32(rec_addr);
+        const char* src = xcb + (uint64_t)u * ldxb;
+        const uint32_t dst = data_s + (uint32_t)slot * SLOT;
+        const bool off = e >= nedges;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) cp_async16(dst + (uint32_t)j * 512u, src + 128 * j, off || !qv[j]);
+      };
+      auto put_row = [&](float* rowq, int width, const float* v) {
 #pragma unroll
         for (int j = 0; j < NQ; ++j)
-          if (c + 4 * L * j < width && qv[j])
-            __stcs(reinterpret_cast<float4*>(rowp + c + 4 * L * j),
-                   make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+          if (FULL || (c + 32 * j < width && qv[j]))
+            __stcs(reinterpret_cast<float4*>(rowq + c + 32 * j),
+                   make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       };
 
-      int4 nx_rec;
-      int nx_row;
-      load_records(0, nx_rec, nx_row);
-      for (int off = 0; off < maxn; off += LPR) {
-        const int my_idx = nx_rec.x, my_ef = nx_rec.y, my_row = nx_row;
-        const float my_a = __int_as_float(nx_rec.z), my_b = __int_as_float(nx_rec.w);
-        load_records(off + LPR, nx_rec, nx_row);
-        const int cnt = min(LPR, maxn - off);
-        const int mylen = nedges - off;
+      // prologue: two record chunks, then the first RS gathered rows (one commit group each)
+      fetch_chunk(0);
+      fetch_chunk(LPR);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < RS; ++i) {
+        issue(i, rec_g + (uint32_t)i * 16u, i);
+        cp_async_commit();
+      }
 
-        auto issue = [&](int t, int slot) {
-          const uint32_t u = (uint32_t)__shfl_sync(0xffffffffu, my_idx, t, LPR);
-          const float* src = xc + u * ldx32;
-          const uint32_t dst = ring_s + (uint32_t)slot * (uint32_t)(NQ * 32 * 16);
-          const bool off_row = t >= mylen;
+      for (int t = 0; t < maxn; t += RS) {
+        if ((t & (LPR - 1)) == 0) fetch_chunk(t + 2 * LPR);  // joins the first group committed below
+        const uint32_t rbase = rec_g + (((uint32_t)t & rmask) << 4);
+        const uint32_t ibase = rec_g + (((uint32_t)(t + RS) & rmask) << 4);
+        const uint32_t wbase = row_g + (((uint32_t)t & rmask) << 2);
 #pragma unroll
-          for (int j = 0; j < NQ; ++j) cp_async16(dst + (uint32_t)j * (32u * 16u), src + 4 * L * j, off_row || !qv[j]);
-        };
-#pragma unroll
-        for (int i = 0; i < RS - 1; ++i) {
-          if (i < cnt) issue(i, i);
-          cp_async_commit();
-        }
-        int st = 0, fill = RS - 1;
-        for (int t = 0; t < cnt; ++t) {
-          if (t + RS - 1 < cnt) issue(t + RS - 1, fill);
-          fill = fill + 1 == RS ? 0 : fill + 1;
-          cp_async_commit();
-          const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
-          const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
-          const float B = __shfl_sync(0xffffffffu, my_b, t, LPR);
+        for (int j = 0; j < RS; ++j) {
+          // groups committed so far: RS + t + j; all but the last RS - 1 are complete, i.e. the row of edge
+          // t + j and every record chunk up to the one edge t + j + RS lives in
           cp_async_wait<RS - 1>();
+          __syncwarp();  // records are written by other lanes of the group
+          const int4 rc = lds128(rbase + (uint32_t)j * 16u);
+          const int ef = rc.y;
+          const float A = __int_as_float(rc.z), B = __int_as_float(rc.w);
+          const uint32_t slot_s = data_s + (uint32_t)j * SLOT;
+          uint32_t q[4 * NB];
 #pragma unroll
-          for (int b = 0; b < 2 * NBG; ++b) {
-            const int g = b / NBG, m = b % NBG;  // 64-channel half group, block within it
-            float w[8];
-            const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk0 + (uint32_t)(8 * g + L * m), smp, p.key.c3, p);
-            const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
+          for (int g = 0; g < NB; ++g) {
+            const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk0 + (uint32_t)(8 * g), smp, p.key.c3, p);
+            q[4 * g] = r4.x; q[4 * g + 1] = r4.y; q[4 * g + 2] = r4.z; q[4 * g + 3] = r4.w;
+          }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+          for (int g = 0; g < NB; ++g) {
+            float w[8], kept[INNORM ? 8 : 1];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float xl = __uint_as_float(__byte_perm(q[4 * g + i], kf, 0x7610));  // 2^23 + h_lo
+              const float xh = __uint_as_float(__byte_perm(q[4 * g + i], kf, 0x7632));  // 2^23 + h_hi
               if (KIND == STAG_NOISE_NORMAL) {
-                float rad, cs, sn;
-                bm_parts(q[j], rad, cs, sn);
-                const float rb = rad * B;
-                w[2 * j] = fmaf(cs, rb, A);
-                w[2 * j + 1] = fmaf(sn, rb, A);
+                const float u1 = fmaf(xl, 1.52587890625e-05f, -127.99999237060547f);      // (h_lo + 1/2) / 65536
+                const float rb = mufu_sqrt(-mufu_lg2(u1)) * B;                             // B' carries sqrt(2 ln 2)
+                const float ang = fmaf(xh, 9.58738019107841e-05f, -804.2476806640625f);   // 2 pi (h_hi + 1/2) / 65536
+                w[2 * i] = fmaf(mufu_cos(ang), rb, A);
+                w[2 * i + 1] = fmaf(mufu_sin(ang), rb, A);
               } else if (KIND == STAG_NOISE_UNIFORM) {
-                w[2 * j] = fmaf(half_uniform<false>(q[j]), B, A);
-                w[2 * j + 1] = fmaf(half_uniform<true>(q[j]), B, A);
+                w[2 * i] = fmaf(fmaf(xl, 1.52587890625e-05f, -128.0f), B, A);
+                w[2 * i + 1] = fmaf(fmaf(xh, 1.52587890625e-05f, -128.0f), B, A);
               } else {
-                w[2 * j] = half_uniform<false>(q[j]) < A ? B : 0.f;
-                w[2 * j + 1] = half_uniform<true>(q[j]) < A ? B : 0.f;
+                const bool k0 = fmaf(xl, 1.52587890625e-05f, -128.0f) < A, k1 = fmaf(xh, 1.52587890625e-05f, -128.0f) < A;
+                w[2 * i] = k0 ? B : 0.f;
+                w[2 * i + 1] = k1 ? B : 0.f;
+                if (INNORM) {
+                  kept[INNORM ? 2 * i : 0] = k0 ? 1.0f : 0.0f;
+                  kept[INNORM ? 2 * i + 1 : 0] = k1 ? 1.0f : 0.0f;
+                }
               }
             }
-            // the block's slots 0..3 / 4..7 are the lane's quads j = g*(16/L) + m + h*(8/L), h = 0 / 1
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int j = g * (16 / L) + m + h * NBG;
-              const float4 x4 = my_ring[st * (NQ * 32) + j * 32];
-              float* a4 = acc + 4 * j;
+              const int jq = 2 * g + h;
+              const float4 x4 = lds128f(slot_s + (uint32_t)jq * 512u);
+              float* a4 = acc + 4 * jq;
               a4[0] = fmaf(w[4 * h + 0], x4.x, a4[0]);
               a4[1] = fmaf(w[4 * h + 1], x4.y, a4[1]);
               a4[2] = fmaf(w[4 * h + 2], x4.z, a4[2]);
               a4[3] = fmaf(w[4 * h + 3], x4.w, a4[3]);
+              if (INNORM && t + j < nedges) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cntw[INNORM ? 4 * jq + i : 0] += kept[INNORM ? 4 * h + i : 0];
+              }
             }
           }
-          const bool row_done = ef < 0 && part_slot < 0 && t < mylen;
-          if (row_done) {
-            const int rw = __shfl_sync(gmask, my_row, t, LPR);
-            put_row(outs + (int64_t)rw * p.ldo, p.D);
-          }
+          if (INNORM && t + j < nedges) ++row_edges;
+          if (ef < 0 && t + j < rowlim) {  // last edge of a row: write it, start the next one
+            const int rw = lds32(wbase + (uint32_t)j * 4u);
+            if (INNORM) {
+              float sc[NA];
 #pragma unroll
-          for (int j = 0; j < 4 * NQ; ++j) acc[j] = row_done ? 0.f : acc[j];
-          st = st + 1 == RS ? 0 : st + 1;
+              for (int i = 0; i < NA; ++i) {
+                // both are small integers: the fast division is exact to 2 ulp
+                sc[i] = cntw[INNORM ? i : 0] != 0.f ? __fdividef((float)row_edges, cntw[INNORM ? i : 0]) : 1.0f;
+                acc[i] *= sc[i];
+                cntw[INNORM ? i : 0] = 0.f;
+              }
+              row_edges = 0;
+              if (p.norm_scale_out) put_row(p.norm_scale_out + ((int64_t)s * p.N + rw) * p.K, p.K, sc);
+            }
+            put_row(outs + (int64_t)rw * p.ldo, p.D, acc);
+#pragma unroll
+            for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+          }
+          // the slot just consumed takes the row of edge t + j + RS
+          issue(t + j + RS, ibase + (uint32_t)j * 16u, j);
+          cp_async_commit();
         }
       }
-      if (part_slot >= 0) put_row(p.part_acc + ((int64_t)s * p.num_hub_segs + part_slot) * D8, D8);
+      cp_async_wait<0>();
+      __syncwarp();
+      if (part_slot >= 0) {  // hub segment: its partial sum, combined by hub_finalize_kernel
+        const int64_t o = ((int64_t)s * p.num_hub_segs + part_slot) * D8;
+        put_row(p.part_acc + o, D8, acc);
+        if (INNORM) put_row(p.part_w + o, D8, cntw);
+      }
     }
   }
-  cp_async_wait<0>();
 }
 
 // ---- streaming gradient kernel ---------------------------------------------------------------------
@@ -1509,76 +1375,54 @@ static int launch_vec(const AggParams& p, bool vec, int grid, size_t smem, cudaS
   return STAG_OK;
 }
 
+// Launch of the streaming hot kernel (records, empty rows, kernel) for one instantiation.
+template <int KIND, int NB, bool FULL, bool INNORM>
+static int launch_stream_inst(const AggParams& q, cudaStream_t stream) {
+  const int RPW = 32 >> q.lpr_log2;
+  const int64_t witems = (int64_t)((q.num_hub_segs + q.num_items + RPW - 1) / RPW) * q.S * q.ncb;
+  const int64_t nctas = (witems + AGG_WARPS - 1) / AGG_WARPS;
+  const int64_t cap = (int64_t)num_sms() * s3_min_blocks(NB, INNORM);
+  const int grid = (int)(nctas < 1 ? 1 : (nctas < cap ? nctas : cap));
+  const size_t smem = (size_t)AGG_WARPS * s3_warp_bytes(NB);
+  if (q.E > 0) {
+    edge_record_kernel<KIND><<<(unsigned)((q.E + 255) / 256), 256, 0, stream>>>(q, const_cast<int4*>(q.rec), 2);
+    STAG_LAUNCH_CHECK();
+  }
+  zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(q);
+  STAG_LAUNCH_CHECK();
+  STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<KIND, NB, FULL, INNORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+  agg_stream_kernel<KIND, NB, FULL, INNORM><<<grid, AGG_THREADS, smem, stream>>>(q);
+  STAG_LAUNCH_CHECK();
+  return STAG_OK;
+}
+
+// NB = 2 (16 channels per lane) when the rows are made of 128-channel groups, else NB = 1.
+template <int KIND, bool INNORM>
+static int launch_stream(const AggParams& p, cudaStream_t stream) {
+  AggParams q = p;
+  const int width = p.D < p.cw ? p.D : p.cw;
+#ifndef STAG_INNORM_NB
+#define STAG_INNORM_NB 2
+#endif
+  const bool nb2 = p.dpad % 128 == 0 && p.cw % 128 == 0 && (!INNORM || STAG_INNORM_NB == 2);
+  const int nb = nb2 ? 2 : 1;
+  q.lpr_log2 = lpr_log2_for((blocks_for(width) + nb - 1) / nb);
+  if (q.lpr_log2 < 3) q.lpr_log2 = 3;  // a group of 8 lanes owns one 64 NB-channel group
+  const bool full = p.D % (64 * nb) == 0 && p.ncb == 1 && p.cw == p.dpad;
+  if (nb2) return full ? launch_stream_inst<KIND, 2, true, INNORM>(q, stream) : launch_stream_inst<KIND, 2, false, INNORM>(q, stream);
+  return full ? launch_stream_inst<KIND, 1, true, INNORM>(q, stream) : launch_stream_inst<KIND, 1, false, INNORM>(q, stream);
+}
+
 template <int KIND, bool GRADS>
 static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t smem, cudaStream_t stream) {
-  if (!GRADS && psh == 0 && !p.relu && p.in_norm && KIND == STAG_NOISE_BERNOULLI && vec && p.items && p.erow &&
-      p.eidf && p.ncols * p.ldx < (1ll << 31) && (p.norm_scale_out == nullptr || p.K == p.D)) {
-    const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * STREAM_U * 64 * sizeof(float4);
-    STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<STAG_NOISE_BERNOULLI, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-    const int RPW = 32 >> p.lpr_log2;
-    const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S * p.ncb;
-    const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
-    const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * STAG_STREAM_MINBLOCKS ? ctas : num_sms() * STAG_STREAM_MINBLOCKS));
-    if (p.E > 0) {
-      edge_record_kernel<STAG_NOISE_BERNOULLI><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
-          p, const_cast<int4*>(p.rec), 0);
-      STAG_LAUNCH_CHECK();
-    }
-    zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
-    STAG_LAUNCH_CHECK();
-    agg_stream_kernel<STAG_NOISE_BERNOULLI, true><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
-    STAG_LAUNCH_CHECK();
-    return STAG_OK;
-  }
-  if (!GRADS && psh == 0 && !p.relu && !p.in_norm) {
-    // streaming hot kernel: 128-bit rows, row offsets of the gathered operand fit 32 bits
-    static const bool wide_off = getenv("STAG_NO_WIDE") != nullptr;  // tuning knob
-    if (vec && p.items && p.erow && p.eidf && p.ncols * p.ldx < (1ll << 31) && p.dpad % 128 == 0 &&
-        p.cw % 128 == 0 && !wide_off) {
-      // NB Philox blocks (8 * NB channels) per lane: lanes per row = blocks of a chunk / NB
-      // L = 8 lanes per 128 channels (2 blocks per lane); L = 4 (32 channels per lane) was measured slower
-      // (2.7 vs 1.95 ms per launch at the arxiv shape: register-bound) and is not instantiated
-      const int nb = 2;
-      AggParams q = p;
-      q.lpr_log2 = lpr_log2_for((blocks_for(p.D < p.cw ? p.D : p.cw) + nb - 1) / nb);
-      const size_t ring_bytes = (size_t)AGG_WARPS * RING2_STAGES * (2 * nb * 32) * sizeof(float4);
-      const int RPW = 32 >> q.lpr_log2;
-      const int64_t warp_items = (int64_t)((q.num_hub_segs + q.num_items + RPW - 1) / RPW) * q.S * q.ncb;
-      const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
-      const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * 2 ? ctas : num_sms() * 2));
-      if (q.E > 0) {
-        edge_record_kernel<KIND><<<(unsigned)((q.E + 255) / 256), 256, 0, stream>>>(q, const_cast<int4*>(q.rec), 0);
-        STAG_LAUNCH_CHECK();
-      }
-      zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(q);
-      STAG_LAUNCH_CHECK();
-      STAG_CUDA(cudaFuncSetAttribute(agg_stream2_kernel<KIND, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)ring_bytes));
-      agg_stream2_kernel<KIND, 8><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(q);
-      STAG_LAUNCH_CHECK();
-      return STAG_OK;
-    }
-    if (vec && p.items && p.erow && p.eidf && p.ncols * p.ldx < (1ll << 31)) {
-      const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * STREAM_U * 64 * sizeof(float4);
-      STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)ring_bytes));
-      const int RPW = 32 >> p.lpr_log2;
-      const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S * p.ncb;
-      const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
-      const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * STAG_STREAM_MINBLOCKS ? ctas : num_sms() * STAG_STREAM_MINBLOCKS));
-      if (p.E > 0) {
-        edge_record_kernel<KIND><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(p, const_cast<int4*>(p.rec), 0);
-        STAG_LAUNCH_CHECK();
-      }
-      zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
-      STAG_LAUNCH_CHECK();
-      agg_stream_kernel<KIND><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
-      STAG_LAUNCH_CHECK();
-      return STAG_OK;
-    }
-    return launch_vec<2, KIND, 0, false, true>(p, vec, grid, smem, stream);
-  }
+  // streaming hot kernel: 128-bit rows, row offsets of the gathered operand fit 32 bits
+  const bool stream_ok = !GRADS && psh == 0 && !p.relu && vec && p.items && p.erow && p.eidf && p.rec &&
+                         p.ncols * p.ldx < (1ll << 31);
+  if (stream_ok && p.in_norm && KIND == STAG_NOISE_BERNOULLI && (p.norm_scale_out == nullptr || p.K == p.D))
+    return launch_stream<STAG_NOISE_BERNOULLI, true>(p, stream);
+  if (stream_ok && !p.in_norm) return launch_stream<KIND, false>(p, stream);
+  if (!GRADS && psh == 0 && !p.relu && !p.in_norm) return launch_vec<2, KIND, 0, false, true>(p, vec, grid, smem, stream);
   switch (psh) {
     case 0: return launch_vec<2, KIND, 0, GRADS>(p, vec, grid, smem, stream);
     case 1: return launch_vec<2, KIND, 1, GRADS>(p, vec, grid, smem, stream);
@@ -1650,6 +1494,7 @@ static void fill_noise(AggParams& p, const StagNoise* n, int D) {
   p.p1 = n->p1;
   p.ext = n->external;
   p.key = make_key(n->seed, n->offset);
+  p.kf = 0x4B000000u;
   for (int r = 0; r < kPhiloxRounds; ++r) {
     p.rk[2 * r] = p.key.k0 + (uint32_t)r * 0x9E3779B9u;
     p.rk[2 * r + 1] = p.key.k1 + (uint32_t)r * 0xBB67AE85u;
