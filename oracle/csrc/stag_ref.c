@@ -92,7 +92,7 @@ static inline void box_muller(uint32_t r, float* z0, float* z1) {
 
 /* raw variates of (edge, oct, sample): 8 standard normals or 8 U[0,1) */
 static inline void raw8(int kind, uint32_t e, uint32_t q, uint32_t s, uint64_t seed, uint64_t offset, float v[8]) {
-  uint32_t c[4] = {e, q, s, (uint32_t)(offset & 0xffffffffu)};
+  uint32_t c[4] = {q, e, s, (uint32_t)(offset & 0xffffffffu)};
   philox4x32(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32));
   for (int i = 0; i < 4; ++i) {
     if (kind == K_NORMAL) {

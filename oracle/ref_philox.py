@@ -12,7 +12,7 @@ The round function is pinned against the Random123 known-answer vectors at 10 ro
 (tests/test_oracle_cpu.py); 7 is the smallest Crush-resistant round count (ibid., table 2).
 
 Counter / key layout (one 128-bit block b = 8 channels of one edge):
-    ctr = (eid, b, sample, offset_lo)      key = (seed_lo, seed_hi ^ offset_hi)
+    ctr = (b, eid, sample, offset_lo)      key = (seed_lo, seed_hi ^ offset_hi)
     channels of block b: c(b)+{0..3} and c(b)+32+{0..3}, c(b) = 64*(b//8) + 4*(b%8)
 Each output word r_i (i = 0..3) gives slot 2i (from its low 16 bits h_lo) and slot 2i+1 (from its
 high 16 bits h_hi); slot j < 4 is channel c(b)+j, slot j >= 4 is channel c(b)+32+(j-4):
@@ -66,7 +66,7 @@ def raw_block(eid, q, sample, seed, offset):
     offset = int(offset) & 0xFFFFFFFFFFFFFFFF
     k0 = seed & 0xFFFFFFFF
     k1 = (seed >> 32) ^ (offset >> 32)
-    return philox4x32(eid, q, sample, np.uint32(offset & 0xFFFFFFFF), k0, k1)
+    return philox4x32(q, eid, sample, np.uint32(offset & 0xFFFFFFFF), k0, k1)
 
 
 def n_blocks(K):

@@ -146,7 +146,7 @@ __device__ __forceinline__ float sum8(const float (&v)[8]) {
 template <int KIND>
 __device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t smp, const PhiloxKey& key, float A,
                                            float B, float (&w)[8]) {
-  const uint4 r = philox4x32<kPhiloxRounds>(eid, oct, smp, key.c3, key.k0, key.k1);
+  const uint4 r = philox4x32<kPhiloxRounds>(oct, eid, smp, key.c3, key.k0, key.k1);
   const uint32_t q[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(AGG_THREADS, s3_min_blocks(NB, INNORM)) agg_st
           uint32_t q[4 * NB];
 #pragma unroll
           for (int g = 0; g < NB; ++g) {
-            const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk0 + (uint32_t)(8 * g), smp, p.key.c3, p);
+            const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
             q[4 * g] = r4.x; q[4 * g + 1] = r4.y; q[4 * g + 2] = r4.z; q[4 * g + 3] = r4.w;
           }
 #pragma unroll
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
         const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
         float raw[8];
         if (BODY == 0) {
-          const uint4 r4 = philox_rk((uint32_t)(ef & 0x7fffffff), blk, smp, p.key.c3, p);
+          const uint4 r4 = philox_rk(blk, (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
           const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
