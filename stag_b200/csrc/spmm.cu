@@ -222,7 +222,7 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, in
   const int row = __ldg(p.erow + j);
   float sc = p.gscale ? __ldg(p.gscale + idx) : 1.0f;
   if (p.rscale && __ldg(p.indptr + row + 1) - __ldg(p.indptr + row) <= kHubThreshold) sc *= __ldg(p.rscale + row);
-  if (scales_only == 1) {  // gradient kernel: the parameters stay in registers, only the two scalings are folded
+  if (scales_only == 1 || KIND == STAG_NOISE_NONE) {  // gradient kernel: the parameters stay in registers, only the two scalings are folded
     rec[j] = make_int4(idx, ef, __float_as_int(sc), 0);
     return;
   }
@@ -451,16 +451,22 @@ __global__ void __launch_bounds__(AGG_THREADS, s3_min_blocks(NB, INNORM)) agg_st
           const float A = __int_as_float(rc.z), B = __int_as_float(rc.w);
           const uint32_t slot_s = data_s + (uint32_t)j * SLOT;
           uint32_t q[4 * NB];
+          if (KIND != STAG_NOISE_NONE) {
 #pragma unroll
-          for (int g = 0; g < NB; ++g) {
-            const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
-            q[4 * g] = r4.x; q[4 * g + 1] = r4.y; q[4 * g + 2] = r4.z; q[4 * g + 3] = r4.w;
+            for (int g = 0; g < NB; ++g) {
+              const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
+              q[4 * g] = r4.x; q[4 * g + 1] = r4.y; q[4 * g + 2] = r4.z; q[4 * g + 3] = r4.w;
+            }
           }
 #pragma unroll
           for (int g = 0; g < NB; ++g) {
             float w[8], kept[INNORM ? 8 : 1];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+              if (KIND == STAG_NOISE_NONE) {  // plain copy_u / sum: the folded scale is the weight
+                w[2 * i] = w[2 * i + 1] = A;
+                continue;
+              }
               const float xl = __uint_as_float(__byte_perm(q[4 * g + i], kf, 0x7610));  // 2^23 + h_lo
               const float xh = __uint_as_float(__byte_perm(q[4 * g + i], kf, 0x7632));  // 2^23 + h_hi
               if (KIND == STAG_NOISE_NORMAL) {
@@ -547,28 +553,37 @@ __global__ void __launch_bounds__(AGG_THREADS, s3_min_blocks(NB, INNORM)) agg_st
 //   PG = false           the two-sum FORWARD for per-channel parameters (or relu): out = P0*a0 + P1'*a1
 //   BODY = 1 (PG false)  per-edge weights (no noise / external [E,1] / generated K == 1 with scalar
 //                        parameters): the lane that loads an edge record computes its weight, out = a0
+// Shared-memory layout per warp: [RS][NQS quads][32 lanes] float4 (NQS = 4 with PG: gathered row + the row's own
+// features), then the record and row rings of the hot kernel; the parameter-gradient staging follows the warps.
+__host__ __device__ constexpr uint32_t s2_warp_bytes(bool pg) { return (uint32_t)(S3_RS * (pg ? 4 : 2) * 512) + S3_REC_BYTES + S3_ROW_BYTES; }
+
 template <int KIND, int BODY, bool PG>
 __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const AggParams p) {
-  extern __shared__ float4 ring[];  // [AGG_WARPS][RING_STAGES][2 operands][2][32], then float staging
+  extern __shared__ float4 ring[];
+  constexpr int RS = S3_RS, NQS = PG ? 4 : 2;
+  constexpr uint32_t SLOT = NQS * 512u, DATA_BYTES = RS * SLOT, WARP_BYTES = s2_warp_bytes(PG);
+  constexpr float kRad = 1.1774100225154747f;  // sqrt(2 ln 2): the radius is taken as sqrt(-lg2 u1)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int LPR = 1 << p.lpr_log2;
+  const int LPR = 1 << p.lpr_log2;  // >= 8 (launcher)
   const int RPW = 32 >> p.lpr_log2;
   const int sub = lane >> p.lpr_log2;
   const int sl = lane & (LPR - 1);
   const int D8 = p.dpad;
-  const uint32_t gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-  // ring slot = [gathered row: 2 x 32 float4][x row: 2 x 32 float4]
-  const float4* my_ring = ring + (size_t)warp * RING_STAGES * 128 + lane;
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(my_ring);
-  float* stage = reinterpret_cast<float*>(ring + (size_t)AGG_WARPS * RING_STAGES * 128);  // [AGG_WARPS][2][dpad]
+  const uint32_t warp_s = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)warp * WARP_BYTES;
+  const uint32_t data_s = warp_s + (uint32_t)lane * 16u;
+  const uint32_t rmask = (uint32_t)(S3_NBUF * LPR) - 1u;
+  const uint32_t rec_g = warp_s + DATA_BYTES + (uint32_t)(sub * S3_NBUF * LPR) * 16u + (uint32_t)sub * 16u;
+  const uint32_t row_g = warp_s + DATA_BYTES + S3_REC_BYTES + (uint32_t)(sub * S3_NBUF * LPR) * 4u + (uint32_t)sub * 4u;
+  float* stage = reinterpret_cast<float*>(reinterpret_cast<char*>(ring) + (size_t)AGG_WARPS * WARP_BYTES);  // [AGG_WARPS][2][dpad]
+  const uint32_t kf = p.kf;
 
   const int n_items = p.num_hub_segs + p.num_items;
   const int IG = (n_items + RPW - 1) / RPW;
   const int64_t total = (int64_t)IG * p.S;
   const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
 
-  // this lane's channels (single chunk: dpad <= LPR * 8) and parameters
+  // this lane's channels (single chunk: dpad <= LPR * 8) and parameters; Normal: P1 carries sqrt(2 ln 2)
   const int c = first_chan(0, sl);
   const bool qvalid = c < p.D;
   const bool qvalid2 = c + 32 < p.D;
@@ -582,24 +597,25 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
     P0[i] = BODY == 0 ? __ldg(p.p0 + pi) : 1.0f;
     P1[i] = BODY == 0 ? __ldg(p.p1 + pi) : 0.0f;
     if (BODY == 0 && KIND == STAG_NOISE_UNIFORM) P1[i] -= P0[i];  // w = low + u * (high - low)
+    if (BODY == 0 && KIND == STAG_NOISE_NORMAL) P1[i] *= kRad;
     d0[i] = d1[i] = 0.f;
   }
-  const uint32_t ldx32 = (uint32_t)p.ldx, ldxr32 = (uint32_t)p.ldxr;
+  const uint32_t ldxb = (uint32_t)p.ldx * 4u, ldxrb = (uint32_t)p.ldxr * 4u;
 
   for (int64_t item = (int64_t)blockIdx.x * AGG_WARPS + warp; item < total; item += total_warps) {
     const int s = (int)(item / IG);
     const int gi = (int)(item - (int64_t)s * IG) * RPW + sub;
-    int e0 = 0, e1 = 0, part_slot = -1;
+    int e0 = 0, e1 = 0, part_slot = -1, hub_row = 0;
     if (gi < p.num_hub_segs) {
       int lo = 0, hi = p.num_hubs;
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (__ldg(p.hub_seg_ptr + mid) <= gi) lo = mid; else hi = mid;
       }
-      const int row = __ldg(p.hub_rows + lo);
+      hub_row = __ldg(p.hub_rows + lo);
       const int k = gi - __ldg(p.hub_seg_ptr + lo);
-      e0 = __ldg(p.indptr + row) + k * kHubSegment;
-      e1 = min(e0 + kHubSegment, __ldg(p.indptr + row + 1));
+      e0 = __ldg(p.indptr + hub_row) + k * kHubSegment;
+      e1 = min(e0 + kHubSegment, __ldg(p.indptr + hub_row + 1));
       part_slot = gi;
     } else if (gi < n_items) {
       const int4 it = __ldg(reinterpret_cast<const int4*>(p.items) + (gi - p.num_hub_segs));
@@ -607,96 +623,119 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
       e1 = it.w >= 0 ? it.w : it.z;
     }
     const int nedges = e1 - e0;
+    const int rowlim = part_slot < 0 ? nedges : 0;
     int maxn = nedges;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
 
-    const float* gs_ = p.x + (int64_t)s * p.x_ss + (qvalid ? c : 0);         // gathered operand (dOut), lane's column
-    const float* xr_ = PG ? p.xrow + (int64_t)s * p.xr_ss + (qvalid ? c : 0) : nullptr;  // the rows' own features
+    const char* gsb = reinterpret_cast<const char*>(p.x + (int64_t)s * p.x_ss + (qvalid ? c : 0));  // gathered operand
+    const char* xrb = PG ? reinterpret_cast<const char*>(p.xrow + (int64_t)s * p.xr_ss + (qvalid ? c : 0)) : nullptr;
     float* outs = p.out ? p.out + (int64_t)s * p.out_ss : nullptr;
     const uint32_t smp = (uint32_t)(p.sample_base + s);
+    const int4* recp = p.rec + e0;
+    const int32_t* rowp = p.erow + e0;
     float a0[8], a1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
 
-    // records: {neighbour, eid | flush << 31, A, -}; flush = last edge of its row, or of a hub segment
-    auto load_records = [&](int off, int4& rc, int& rw) {
-      rc = make_int4(0, 0, 0, 0);
-      rw = 0;
-      if (off + sl < nedges) {
-        rc = __ldg(p.rec + e0 + off + sl);
-        rw = __ldg(p.erow + e0 + off + sl);
-        if (part_slot >= 0) rc.y = (rc.y & 0x7fffffff) | (off + sl == nedges - 1 ? (int)0x80000000 : 0);
-        if (BODY == 1 && p.kind != STAG_NOISE_NONE) {  // per-edge weight of this (edge, sample), folded into A
-          const int eid = rc.y & 0x7fffffff;
-          float w;
-          if (p.kind == STAG_NOISE_EXTERNAL) {
-            w = __ldg(p.ext + (int64_t)s * p.E + eid);
-          } else {
-            w = transform_rt(p.kind, raw_first(p.kind, (uint32_t)eid, smp, p.key), __ldg(p.p0),
-                             p.p1 ? __ldg(p.p1) : 0.f);
-          }
-          if (p.relu) w = fmaxf(w, 0.f);
-          rc.z = __float_as_int(__int_as_float(rc.z) * w);
+    // records {neighbour, eid | last << 31, A, -} and rows -> rings (zeros past the end of the item)
+    auto fetch_chunk = [&](int first) {
+      const int e = first + sl;
+      const uint32_t pos = (uint32_t)e & rmask;
+      const bool off = e >= nedges;
+      cp_async16(rec_g + pos * 16u, recp + (off ? 0 : e), off);
+      cp_async4(row_g + pos * 4u, rowp + (off ? 0 : e), off);
+    };
+    // BODY 1 with a per-edge weight (external [E,1] or generated K == 1): the lane that owns ring position
+    // first + sl folds the weight of its (edge, sample) into A once the chunk has landed
+    auto weight_chunk = [&](int first) {
+      if (BODY == 1 && p.kind != STAG_NOISE_NONE && first + sl < nedges) {
+        const uint32_t a = rec_g + (((uint32_t)(first + sl) & rmask) << 4);
+        const int eid = lds32(a + 4u) & 0x7fffffff;
+        float w;
+        if (p.kind == STAG_NOISE_EXTERNAL) {
+          w = __ldg(p.ext + (int64_t)s * p.E + eid);
+        } else {
+          w = transform_rt(p.kind, raw_first(p.kind, (uint32_t)eid, smp, p.key), __ldg(p.p0), p.p1 ? __ldg(p.p1) : 0.f);
         }
+        if (p.relu) w = fmaxf(w, 0.f);
+        const float A = __int_as_float(lds32(a + 8u)) * w;
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + 8u), "r"(__float_as_int(A)) : "memory");
       }
     };
-    int4 nx_rec;
-    int nx_row;
-    load_records(0, nx_rec, nx_row);
-    for (int off = 0; off < maxn; off += LPR) {
-      const int my_idx = nx_rec.x, my_ef = nx_rec.y, my_row = nx_row;
-      const float my_a = __int_as_float(nx_rec.z);
-      load_records(off + LPR, nx_rec, nx_row);
-      const int cnt = min(LPR, maxn - off);
-      const int mylen = nedges - off;
-
-      auto issue = [&](int t, int slot) {
-        const uint32_t u = (uint32_t)__shfl_sync(0xffffffffu, my_idx, t, LPR);
-        const int eft = PG ? __shfl_sync(0xffffffffu, my_ef, t, LPR) : 0;
-        const uint32_t rw = PG ? (uint32_t)__shfl_sync(0xffffffffu, my_row, t, LPR) : 0u;
-        const float* src = gs_ + u * ldx32;
-        const uint32_t dst = ring_s + (uint32_t)slot * (128u * 16u);
-        const bool off_row = t >= mylen;
-        cp_async16(dst, src, off_row || !qvalid);
-        cp_async16(dst + 32u * 16u, src + 32, off_row || !qvalid2);
-        if (PG && eft < 0 && !off_row) {  // the row ends with this edge: fetch its own feature row as well
-          const float* xs = xr_ + rw * ldxr32;
-          cp_async16(dst + 64u * 16u, xs, !qvalid);
-          cp_async16(dst + 96u * 16u, xs + 32, !qvalid2);
+    auto issue = [&](int e, uint32_t rec_addr, uint32_t row_addr, int slot) {
+      const bool off = e >= nedges;
+      const uint32_t dst = data_s + (uint32_t)slot * SLOT;
+      if (PG) {
+        const int4 r = lds128(rec_addr);
+        const char* src = gsb + (uint64_t)(uint32_t)r.x * ldxb;
+        cp_async16(dst, src, off || !qvalid);
+        cp_async16(dst + 512u, src + 128, off || !qvalid2);
+        if (r.y < 0 && e < rowlim) {  // the row ends with this edge: fetch its own feature row as well
+          const char* xs = xrb + (uint64_t)(uint32_t)lds32(row_addr) * ldxrb;
+          cp_async16(dst + 1024u, xs, !qvalid);
+          cp_async16(dst + 1536u, xs + 128, !qvalid2);
         }
-      };
-#pragma unroll
-      for (int i = 0; i < RING_STAGES - 1; ++i) {
-        if (i < cnt) issue(i, i);
-        cp_async_commit();
+      } else {
+        const char* src = gsb + (uint64_t)(uint32_t)lds32(rec_addr) * ldxb;
+        cp_async16(dst, src, off || !qvalid);
+        cp_async16(dst + 512u, src + 128, off || !qvalid2);
       }
-      int st = 0, fill = RING_STAGES - 1;
-      for (int t = 0; t < cnt; ++t) {
-        if (t + RING_STAGES - 1 < cnt) issue(t + RING_STAGES - 1, fill);
-        fill = ring_next(fill);
-        cp_async_commit();
-        const int ef = __shfl_sync(0xffffffffu, my_ef, t, LPR);
-        const float A = __shfl_sync(0xffffffffu, my_a, t, LPR);
+    };
+
+    fetch_chunk(0);
+    fetch_chunk(LPR);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    weight_chunk(0);
+    weight_chunk(LPR);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < RS; ++i) {
+      issue(i, rec_g + (uint32_t)i * 16u, row_g + (uint32_t)i * 4u, i);
+      cp_async_commit();
+    }
+
+    for (int t = 0; t < maxn; t += RS) {
+      if ((t & (LPR - 1)) == 0) {
+        // chunk t / LPR + 2 is requested now; it is complete (and its weights are folded) one chunk later,
+        // LPR - RS edges before its first record is needed
+        if (t > 0) weight_chunk(t + LPR);
+        fetch_chunk(t + 2 * LPR);
+      }
+      const uint32_t rbase = rec_g + (((uint32_t)t & rmask) << 4);
+      const uint32_t ibase = rec_g + (((uint32_t)(t + RS) & rmask) << 4);
+      const uint32_t wbase = row_g + (((uint32_t)t & rmask) << 2);
+      const uint32_t vbase = row_g + (((uint32_t)(t + RS) & rmask) << 2);
+#pragma unroll
+      for (int j = 0; j < RS; ++j) {
+        cp_async_wait<RS - 1>();
+        __syncwarp();
+        const int4 rc = lds128(rbase + (uint32_t)j * 16u);
+        const int ef = rc.y;
+        const float A = __int_as_float(rc.z);
+        const uint32_t slot_s = data_s + (uint32_t)j * SLOT;
         float raw[8];
         if (BODY == 0) {
           const uint4 r4 = philox_rk(blk, (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
           const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (KIND == STAG_NOISE_NORMAL) {
-              float rad, cs, sn;
-              bm_parts(q[j], rad, cs, sn);
-              raw[2 * j] = rad * cs;
-              raw[2 * j + 1] = rad * sn;
+          for (int i = 0; i < 4; ++i) {
+            const float xl = __uint_as_float(__byte_perm(q[i], kf, 0x7610));
+            const float xh = __uint_as_float(__byte_perm(q[i], kf, 0x7632));
+            if (KIND == STAG_NOISE_NORMAL) {  // eps / sqrt(2 ln 2)
+              const float rad = mufu_sqrt(-mufu_lg2(fmaf(xl, 1.52587890625e-05f, -127.99999237060547f)));
+              const float ang = fmaf(xh, 9.58738019107841e-05f, -804.2476806640625f);
+              raw[2 * i] = rad * mufu_cos(ang);
+              raw[2 * i + 1] = rad * mufu_sin(ang);
             } else {
-              raw[2 * j] = half_uniform<false>(q[j]);
-              raw[2 * j + 1] = half_uniform<true>(q[j]);
+              raw[2 * i] = fmaf(xl, 1.52587890625e-05f, -128.0f);
+              raw[2 * i + 1] = fmaf(xh, 1.52587890625e-05f, -128.0f);
             }
           }
         }
-        cp_async_wait<RING_STAGES - 1>();
-        const float4 xa = my_ring[st * 128], xb = my_ring[st * 128 + 32];
+        const float4 xa = lds128f(slot_s), xb = lds128f(slot_s + 512u);
         const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -709,29 +748,15 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
             a1[i] = fmaf(raw[i], y, a1[i]);
           }
         }
-        if (ef < 0 && t < mylen) {  // end of the row (or of the hub segment): group-uniform
-          const int rw = __shfl_sync(gmask, my_row, t, LPR);
-          float xr[8];
-          if (PG) {
-            const float4 ra = my_ring[st * 128 + 64], rb = my_ring[st * 128 + 96];
-            xr[0] = ra.x; xr[1] = ra.y; xr[2] = ra.z; xr[3] = ra.w;
-            xr[4] = rb.x; xr[5] = rb.y; xr[6] = rb.z; xr[7] = rb.w;
-          }
+        if (ef < 0 && t + j < rowlim) {  // end of a row: group-uniform
+          const int rw = lds32(wbase + (uint32_t)j * 4u);
           float dxv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) dxv[i] = BODY == 1 ? a0[i] : fmaf(P1[i], a1[i], P0[i] * a0[i]);
-          if (part_slot >= 0) {
-            // hub segment: partial (row scale applied by hub_finalize_kernel); x scaled here
-            if (PG) {
-              const float rs = p.rscale ? __ldg(p.rscale + rw) : 1.0f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) xr[i] *= rs;
-            }
-            if (outs && qvalid) store8<true, false>(p.part_acc + ((int64_t)s * p.num_hub_segs + part_slot) * D8, c, D8, dxv);
-          } else if (outs && qvalid) {
-            store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, dxv);
-          }
+          if (outs && qvalid) store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, dxv);
           if (PG) {
+            const float4 ra = lds128f(slot_s + 1024u), rb = lds128f(slot_s + 1536u);
+            const float xr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float t1 = xr[i] * a1[i];
@@ -739,23 +764,42 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
               d0[i] += KIND == STAG_NOISE_NORMAL ? xr[i] * a0[i] : xr[i] * a0[i] - t1;
             }
           }
-        }
-        {
-          const bool row_done = ef < 0 && t < mylen;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {  // selects, not a merge of two register copies
-            a0[i] = row_done ? 0.f : a0[i];
-            if (BODY == 0) a1[i] = row_done ? 0.f : a1[i];
-          }
+          for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
         }
-        st = ring_next(st);
+        issue(t + j + RS, ibase + (uint32_t)j * 16u, vbase + (uint32_t)j * 4u, j);
+        cp_async_commit();
+      }
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    if (part_slot >= 0) {
+      // hub segment: partial sums (row scale applied by hub_finalize_kernel); parameter gradients against the
+      // hub row's own features, scaled here
+      float dxv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dxv[i] = BODY == 1 ? a0[i] : fmaf(P1[i], a1[i], P0[i] * a0[i]);
+      if (outs && qvalid) store8<true, false>(p.part_acc + ((int64_t)s * p.num_hub_segs + part_slot) * D8, c, D8, dxv);
+      if (PG && nedges > 0) {
+        float xr[8];
+        load8<true>(p.xrow + (int64_t)s * p.xr_ss + (int64_t)hub_row * p.ldxr, c, p.D, xr);
+        const float rs = p.rscale ? __ldg(p.rscale + hub_row) : 1.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xs = xr[i] * rs, t1 = xs * a1[i];
+          d1[i] += t1;
+          d0[i] += KIND == STAG_NOISE_NORMAL ? xs * a0[i] : xs * a0[i] - t1;
+        }
       }
     }
   }
-  cp_async_wait<0>();
   if (!PG) return;
 
   // ---- parameter-gradient partials: groups of a warp -> warp slice -> CTA row of dp_partial -----------
+  if (KIND == STAG_NOISE_NORMAL) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d1[i] *= kRad;  // a1 was accumulated against eps / sqrt(2 ln 2)
+  }
   for (int o = LPR; o < 32; o <<= 1) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -1432,12 +1476,14 @@ static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t sm
 
 // forward (or dX-only) launches of the two-sum / per-edge-weight streaming kernel
 template <int KIND, int BODY>
-static int launch_stream2(const AggParams& p, cudaStream_t stream) {
+static int launch_stream2(const AggParams& p_, cudaStream_t stream) {
+  AggParams p = p_;
+  if (p.lpr_log2 < 3) p.lpr_log2 = 3;  // record chunks of at least 8 edges (narrow rows leave lanes idle)
   const int RPW = 32 >> p.lpr_log2;
   const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S;
   const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
   const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * 2 ? ctas : num_sms() * 2));
-  const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * 128 * sizeof(float4);
+  const size_t ring_bytes = (size_t)AGG_WARPS * s2_warp_bytes(false);
   if (p.E > 0) {
     edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
         p, const_cast<int4*>(p.rec), 1);
@@ -1458,8 +1504,8 @@ static int launch_agg(const AggParams& p, bool vec, int grid, size_t smem, cudaS
   const bool stream2 = !GRADS && vec && p.items && p.erow && p.eidf && p.rec && !p.in_norm && p.ncb == 1 &&
                        p.dpad <= 256 && p.ncols * p.ldx < (1ll << 31);
   if (stream2) {
-    if (p.kind == STAG_NOISE_NONE || (p.K == 1 && (p.kind == STAG_NOISE_EXTERNAL || p.pshape == STAG_PARAM_SCALAR)))
-      return launch_stream2<0, 1>(p, stream);
+    if (p.kind == STAG_NOISE_NONE) return launch_stream<STAG_NOISE_NONE, false>(p, stream);
+    if (p.K == 1 && (p.kind == STAG_NOISE_EXTERNAL || p.pshape == STAG_PARAM_SCALAR)) return launch_stream2<0, 1>(p, stream);
     if (p.K != 1 && p.pshape <= STAG_PARAM_CHANNEL && (p.pshape == STAG_PARAM_CHANNEL || p.relu)) {
       if (p.kind == STAG_NOISE_NORMAL) return launch_stream2<STAG_NOISE_NORMAL, 0>(p, stream);
       if (p.kind == STAG_NOISE_UNIFORM) return launch_stream2<STAG_NOISE_UNIFORM, 0>(p, stream);
@@ -1688,11 +1734,12 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   int sgrid = grid;
   if (stream_ok) {
     p.rec = (const int4*)((char*)ws + L.rec);
+    if (p.lpr_log2 < 3) p.lpr_log2 = 3;  // record chunks of at least 8 edges
     const int RPW = 32 >> p.lpr_log2;
     const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S;
     const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
     sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * 2 ? ctas : num_sms() * 2));
-    const size_t ring_bytes = (size_t)AGG_WARPS * RING_STAGES * 128 * sizeof(float4) + smem;
+    const size_t ring_bytes = (size_t)AGG_WARPS * s2_warp_bytes(true) + smem;
     if (p.E > 0) {
       edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
           p, const_cast<int4*>(p.rec), 1);
