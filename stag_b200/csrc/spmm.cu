@@ -313,8 +313,11 @@ __device__ __forceinline__ int lds32(uint32_t a) {
   return v;
 }
 
+// 8 warps x 2 CTAs per SM at 128 registers: 10 or 12 warps per CTA (96 / 80 registers) measured slower
+constexpr int S3_THREADS = 256, S3_WARPS = S3_THREADS / 32;
+
 template <int KIND, int NB, bool FULL, bool INNORM>
-__global__ void __launch_bounds__(AGG_THREADS, s3_min_blocks(NB, INNORM)) agg_stream_kernel(const AggParams p) {
+__global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_stream_kernel(const AggParams p) {
   extern __shared__ float4 ring[];
   constexpr int RS = S3_RS, NQ = 2 * NB, GW = 64 * NB, NA = 4 * NQ;
   constexpr uint32_t DATA_BYTES = s3_data_bytes(NB), WARP_BYTES = s3_warp_bytes(NB), SLOT = NQ * 512u;
@@ -336,9 +339,9 @@ __global__ void __launch_bounds__(AGG_THREADS, s3_min_blocks(NB, INNORM)) agg_st
   const int n_items = p.num_hub_segs + p.num_items;
   const int IG = (n_items + RPW - 1) / RPW;  // warp items per (sample, column block)
   const int64_t total = (int64_t)IG * p.S * p.ncb;
-  const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
+  const int64_t total_warps = (int64_t)gridDim.x * S3_WARPS;
 
-  for (int64_t item = (int64_t)blockIdx.x * AGG_WARPS + warp; item < total; item += total_warps) {
+  for (int64_t item = (int64_t)blockIdx.x * S3_WARPS + warp; item < total; item += total_warps) {
     const int64_t outer = item / IG;
     const int gi = (int)(item - outer * IG) * RPW + sub;
     int s, cb;
@@ -1424,10 +1427,10 @@ template <int KIND, int NB, bool FULL, bool INNORM>
 static int launch_stream_inst(const AggParams& q, cudaStream_t stream) {
   const int RPW = 32 >> q.lpr_log2;
   const int64_t witems = (int64_t)((q.num_hub_segs + q.num_items + RPW - 1) / RPW) * q.S * q.ncb;
-  const int64_t nctas = (witems + AGG_WARPS - 1) / AGG_WARPS;
+  const int64_t nctas = (witems + S3_WARPS - 1) / S3_WARPS;
   const int64_t cap = (int64_t)num_sms() * s3_min_blocks(NB, INNORM);
   const int grid = (int)(nctas < 1 ? 1 : (nctas < cap ? nctas : cap));
-  const size_t smem = (size_t)AGG_WARPS * s3_warp_bytes(NB);
+  const size_t smem = (size_t)S3_WARPS * s3_warp_bytes(NB);
   if (q.E > 0) {
     edge_record_kernel<KIND><<<(unsigned)((q.E + 255) / 256), 256, 0, stream>>>(q, const_cast<int4*>(q.rec), 2);
     STAG_LAUNCH_CHECK();
@@ -1436,7 +1439,7 @@ static int launch_stream_inst(const AggParams& q, cudaStream_t stream) {
   STAG_LAUNCH_CHECK();
   STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<KIND, NB, FULL, INNORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-  agg_stream_kernel<KIND, NB, FULL, INNORM><<<grid, AGG_THREADS, smem, stream>>>(q);
+  agg_stream_kernel<KIND, NB, FULL, INNORM><<<grid, S3_THREADS, smem, stream>>>(q);
   STAG_LAUNCH_CHECK();
   return STAG_OK;
 }
@@ -1446,10 +1449,7 @@ template <int KIND, bool INNORM>
 static int launch_stream(const AggParams& p, cudaStream_t stream) {
   AggParams q = p;
   const int width = p.D < p.cw ? p.D : p.cw;
-#ifndef STAG_INNORM_NB
-#define STAG_INNORM_NB 2
-#endif
-  const bool nb2 = p.dpad % 128 == 0 && p.cw % 128 == 0 && (!INNORM || STAG_INNORM_NB == 2);
+  const bool nb2 = p.dpad % 128 == 0 && p.cw % 128 == 0;
   const int nb = nb2 ? 2 : 1;
   q.lpr_log2 = lpr_log2_for((blocks_for(width) + nb - 1) / nb);
   if (q.lpr_log2 < 3) q.lpr_log2 = 3;  // a group of 8 lanes owns one 64 NB-channel group

@@ -1,7 +1,10 @@
 // Micro-benchmark: per-SM throughput of the MUFU (XU pipe) operations the noise generator uses.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mufu_bench mufu_bench.cu ; run on a B200.
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
+
+static int g_threads = 512;  // threads per CTA (argv[1]); 4 CTAs per SM
 
 template <int OP>
 __device__ __forceinline__ float op(float x) {
@@ -43,9 +46,54 @@ __global__ void k(float* out, int iters, float seed) {
   if (s == 12345.678f) out[0] = s;
 }
 
+// the Box-Muller mix: LG2, SQRT, COS, SIN issued round-robin (OP 20), or in runs of 8 of one kind (OP 21)
+template <int OP>
+__global__ void kmix(float* out, int iters, float seed) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = seed + threadIdx.x * 1e-3f + i;
+  for (int it = 0; it < iters; ++it) {
+    if (OP == 20) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 4) {
+        v[i] = op<0>(v[i]); v[i + 1] = op<1>(v[i + 1]); v[i + 2] = op<3>(v[i + 2]); v[i + 3] = op<2>(v[i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = op<0>(v[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = op<1>(v[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = op<3>(v[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = op<2>(v[i]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  if (s == 12345.678f) out[0] = s;
+}
+
+template <int OP>
+void runmix(const char* name, float* d, int sms, double mhz) {
+  const int iters = 2048, threads = g_threads, blocks = sms * 4;
+  kmix<OP><<<blocks, threads>>>(d, 16, 1.5f);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
+  kmix<OP><<<blocks, threads>>>(d, iters, 1.5f);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  const double ops = (double)blocks * threads * iters * (OP == 20 ? 8 : 32);
+  printf("%-14s %8.3f ms  %7.2f Gop/s  %6.2f lanes/clk/SM (at %.0f MHz)\n", name, ms, ops / ms * 1e-6,
+         ops / (ms * 1e-3) / (mhz * 1e6) / sms, mhz);
+}
+
 template <int OP>
 void run(const char* name, float* d, int sms, double mhz) {
-  const int iters = 4096, threads = 512, blocks = sms * 4;
+  const int iters = 4096, threads = g_threads, blocks = sms * 4;
   k<OP><<<blocks, threads>>>(d, 16, 1.5f);
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
@@ -59,7 +107,8 @@ void run(const char* name, float* d, int sms, double mhz) {
          ops / (ms * 1e-3) / (mhz * 1e6) / sms, mhz);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 1) g_threads = atoi(argv[1]);  // threads per CTA, 4 CTAs per SM: 128 -> 4 warps per scheduler
   cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
   int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   const double mhz = clk / 1000.0;
@@ -76,5 +125,7 @@ int main() {
   run<8>("tanh.f16x2", d, pr.multiProcessorCount, mhz);
   run<9>("ex2.f16x2", d, pr.multiProcessorCount, mhz);
   run<10>("ffma", d, pr.multiProcessorCount, mhz);
+  runmix<20>("mix round-robin", d, pr.multiProcessorCount, mhz);
+  runmix<21>("mix runs of 8", d, pr.multiProcessorCount, mhz);
   return 0;
 }
