@@ -28,7 +28,7 @@ for r in rows[hdr + 1:]:
     a[1] += v
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(out_dir, tag + "_launches_summary.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 400   python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 600   python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
     f.write("(cold-cache, serialised launches: compare SHARES, not absolutes)\n\n")
     for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
         f.write("%-100s n=%4d %12.1f us %6.2f%%\n" % (k[:100], a[0], a[1], 100 * a[1] / tot))
