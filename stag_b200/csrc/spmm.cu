@@ -1453,7 +1453,9 @@ static int launch_stream(const AggParams& p, cudaStream_t stream) {
   const int nb = nb2 ? 2 : 1;
   q.lpr_log2 = lpr_log2_for((blocks_for(width) + nb - 1) / nb);
   if (q.lpr_log2 < 3) q.lpr_log2 = 3;  // a group of 8 lanes owns one 64 NB-channel group
-  const bool full = p.D % (64 * nb) == 0 && p.ncb == 1 && p.cw == p.dpad;
+  // FULL (no quad predicates): one column block and every lane of every pass over the channels owns real ones
+  const int pass = (1 << q.lpr_log2) / 8 * 64 * nb;
+  const bool full = p.D % pass == 0 && p.ncb == 1 && p.cw == p.dpad;
   if (nb2) return full ? launch_stream_inst<KIND, 2, true, INNORM>(q, stream) : launch_stream_inst<KIND, 2, false, INNORM>(q, stream);
   return full ? launch_stream_inst<KIND, 1, true, INNORM>(q, stream) : launch_stream_inst<KIND, 1, false, INNORM>(q, stream);
 }

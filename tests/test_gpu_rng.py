@@ -104,7 +104,8 @@ def test_independence_across_edge_channel_sample_offset():
     ("uniform", 0.3, 1.7, False, False), ("bernoulli", 0.6, None, False, True),
     ("bernoulli", 0.6, None, False, False), ("normal", 1.0, 0.4, False, True),
 ])
-@pytest.mark.parametrize("D,K", [(20, 20), (20, 1), (128, 128), (50, 50)])
+@pytest.mark.parametrize("D,K", [(20, 20), (20, 1), (128, 128), (50, 50), (100, 100), (192, 192), (256, 256),
+                                 (384, 384), (640, 640)])
 def test_fused_forward_backward_consume_the_emitted_noise(kind, p0, p1, relu, in_norm, D, K):
     """Fused (noise never stored) == oracle fed the emitted tensor; dX regenerates the same noise."""
     import stag_b200 as sb
