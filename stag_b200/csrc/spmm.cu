@@ -233,6 +233,15 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, in
   if (KIND == STAG_NOISE_NORMAL) { a = sc * pa; b = sc * pb * (scales_only == 2 ? 1.1774100225154747f : 1.0f); }
   else if (KIND == STAG_NOISE_UNIFORM) { a = sc * pa; b = sc * (pb - pa); }
   else { a = pa; b = sc; }
+  if (scales_only == 2 && KIND == STAG_NOISE_UNIFORM) {
+    // the hot kernel multiplies X = 2^23 + h (u = X / 65536 - 128) directly: w = A' + B' X, one FFMA
+    a = fmaf(-128.0f, b, a);
+    b *= 1.52587890625e-05f;
+  }
+  if (scales_only == 2 && KIND == STAG_NOISE_BERNOULLI) {
+    // ... and compares X with 2^23 + ceil(65536 p): h < 65536 p  <=>  h < ceil(65536 p) for integer h (exact)
+    a = 8388608.0f + ceilf(fminf(fmaxf(pa, 0.0f), 1.0f) * 65536.0f);
+  }
   rec[j] = make_int4(idx, ef, __float_as_int(a), __float_as_int(b));
 }
 
@@ -478,11 +487,11 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
                 const float ang = fmaf(xh, 9.58738019107841e-05f, -804.2476806640625f);   // 2 pi (h_hi + 1/2) / 65536
                 w[2 * i] = fmaf(mufu_cos(ang), rb, A);
                 w[2 * i + 1] = fmaf(mufu_sin(ang), rb, A);
-              } else if (KIND == STAG_NOISE_UNIFORM) {
-                w[2 * i] = fmaf(fmaf(xl, 1.52587890625e-05f, -128.0f), B, A);
-                w[2 * i + 1] = fmaf(fmaf(xh, 1.52587890625e-05f, -128.0f), B, A);
-              } else {
-                const bool k0 = fmaf(xl, 1.52587890625e-05f, -128.0f) < A, k1 = fmaf(xh, 1.52587890625e-05f, -128.0f) < A;
+              } else if (KIND == STAG_NOISE_UNIFORM) {  // (A, B) carry the half -> uniform conversion
+                w[2 * i] = fmaf(xl, B, A);
+                w[2 * i + 1] = fmaf(xh, B, A);
+              } else {  // A = 2^23 + ceil(65536 p)
+                const bool k0 = xl < A, k1 = xh < A;
                 w[2 * i] = k0 ? B : 0.f;
                 w[2 * i + 1] = k1 ? B : 0.f;
                 if (INNORM) {
