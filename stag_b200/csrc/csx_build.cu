@@ -251,6 +251,179 @@ __global__ void k_range_close(const int32_t* __restrict__ indptr, int64_t N, con
   items[4 * k + 3] = hub ? -1 : indptr[row1];
 }
 
+
+// ---- minibatch-sized graphs: the whole build in ONE launch ---------------------------------------------
+// A batch of molecule- or PPI-sized graphs (E, N <= kSmallMax) is built by one CTA in shared memory: bitonic
+// sort of (key << 13 | edge id) -- the composite key makes the order total, i.e. the stable order --, degree
+// histogram + scan for the row pointers, and the same hub / row-order / stream-item schedules as the general
+// path (same kernels' semantics, same tests).  ~35 launches and two host synchronisations become one of each.
+constexpr int kSmallMax = 8192;
+constexpr int kSmallThreads = 1024;
+
+__device__ __forceinline__ void bitonic_sort_u32(uint32_t* a, int P) {  // P a power of two, ascending
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += kSmallThreads) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint32_t x = a[i], y = a[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// exclusive scan of v[0..n) in place (n <= kSmallMax), total returned to every thread
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* v, int n, uint32_t* warp_sums) {
+  constexpr int PER = kSmallMax / kSmallThreads;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t loc[PER], sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = tid * PER + k;
+    loc[k] = i < n ? v[i] : 0u;
+    sum += loc[k];
+  }
+  uint32_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = warp_sums[lane], z = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+      if (lane >= o) z += y;
+    }
+    warp_sums[lane] = z - w;           // exclusive prefix of the warp sums
+    if (lane == 31) warp_sums[32] = z;  // total
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[wid] + x - sum;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int i = tid * PER + k;
+    if (i < n) v[i] = run;
+    run += loc[k];
+  }
+  const uint32_t total = warp_sums[32];
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(kSmallThreads) k_build_small(
+    const int64_t* __restrict__ key64, const int64_t* __restrict__ other64, int E, int N, int32_t* __restrict__ indptr,
+    int32_t* __restrict__ indices, int32_t* __restrict__ eid, int32_t* __restrict__ hub_rows,
+    int32_t* __restrict__ hub_seg_ptr, int32_t* __restrict__ row_order, int32_t* __restrict__ items,
+    int32_t* __restrict__ erow, int32_t* __restrict__ eidf, int32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t* comp = sm;                     // [kSmallMax] sort buffer
+  uint32_t* ip = comp + kSmallMax;         // [kSmallMax + 1 (+3: keeps `its` 16-byte aligned)] degrees -> row pointers
+  uint32_t* fa = ip + kSmallMax + 4;       // [kSmallMax] flags / scan
+  uint32_t* fb = fa + kSmallMax;           // [kSmallMax] flags / scan
+  uint32_t* wsum = fb + kSmallMax;         // [33]
+  int4* its = reinterpret_cast<int4*>(wsum + 36);  // stream items before their sort
+  const int tid = threadIdx.x;
+  auto pow2 = [](int n) { int p = 1; while (p < n) p <<= 1; return p; };
+
+  // edges by (key, edge id)
+  const int EP = pow2(E);
+  for (int i = tid; i < EP; i += kSmallThreads) comp[i] = i < E ? ((uint32_t)key64[i] << 13) | (uint32_t)i : 0xffffffffu;
+  for (int v = tid; v <= N; v += kSmallThreads) ip[v] = 0u;
+  __syncthreads();
+  bitonic_sort_u32(comp, EP);
+  for (int j = tid; j < E; j += kSmallThreads) {
+    const uint32_t k = comp[j] >> 13, e = comp[j] & 8191u;
+    eid[j] = (int32_t)e;
+    indices[j] = (int32_t)other64[e];
+    if (erow) erow[j] = (int32_t)k;
+    if (eidf) eidf[j] = (int32_t)(e | ((j + 1 == E || (comp[j + 1] >> 13) != k) ? 0x80000000u : 0u));
+    atomicAdd(&ip[k], 1u);
+  }
+  __syncthreads();
+  block_exclusive_scan(ip, N + 1 <= kSmallMax ? N + 1 : kSmallMax, wsum);  // ip[v] = first stored edge of row v
+  if (N == kSmallMax && tid == 0) ip[N] = (uint32_t)E;
+  __syncthreads();
+  for (int v = tid; v <= N; v += kSmallThreads) indptr[v] = (int32_t)ip[v];
+  auto deg = [&](int v) { return (int)(ip[v + 1] - ip[v]); };
+
+  // rows by decreasing clamped degree, ties by decreasing row
+  if (row_order) {
+    const int NP = pow2(N);
+    for (int v = tid; v < NP; v += kSmallThreads)
+      comp[v] = v < N ? ((uint32_t)min(deg(v), kHubThreshold + 1) << 13) | (uint32_t)v : 0xffffffffu;
+    __syncthreads();
+    bitonic_sort_u32(comp, NP);
+    for (int i = tid; i < N; i += kSmallThreads) row_order[i] = (int32_t)(comp[N - 1 - i] & 8191u);
+    __syncthreads();
+  }
+
+  // hub schedule
+  for (int v = tid; v < N; v += kSmallThreads) {
+    const int d = deg(v);
+    fa[v] = d > kHubThreshold ? 1u : 0u;
+    fb[v] = d > kHubThreshold ? (uint32_t)((d + kHubSegment - 1) / kHubSegment) : 0u;
+  }
+  __syncthreads();
+  const uint32_t nhubs = block_exclusive_scan(fa, N, wsum);
+  const uint32_t nsegs = block_exclusive_scan(fb, N, wsum);
+  for (int v = tid; v < N; v += kSmallThreads)
+    if (deg(v) > kHubThreshold) {
+      hub_rows[fa[v]] = v;
+      hub_seg_ptr[fa[v]] = (int32_t)fb[v];
+    }
+  if (tid == 0) {
+    hub_seg_ptr[nhubs] = (int32_t)nsegs;
+    counts[0] = (int32_t)nhubs;
+    counts[1] = (int32_t)nsegs;
+  }
+  __syncthreads();
+
+  // stream items
+  uint32_t nitems = 0;
+  if (items) {
+    auto starts = [&](int v) {
+      if (v == 0 || (v % kRangeRows) == 0) return true;
+      const int b = (int)ip[v], a = (int)ip[v - 1], c = (int)ip[v + 1];
+      return (c - b > kHubThreshold) || (b - a > kHubThreshold) || (b / kRangeEdges != a / kRangeEdges);
+    };
+    for (int v = tid; v < N; v += kSmallThreads) fa[v] = starts(v) ? 1u : 0u;
+    __syncthreads();
+    nitems = block_exclusive_scan(fa, N, wsum);
+    for (int v = tid; v < N; v += kSmallThreads)
+      if (starts(v)) {
+        its[fa[v]].x = v;
+        its[fa[v]].z = (int)ip[v];
+      }
+    __syncthreads();
+    for (int k = tid; k < (int)nitems; k += kSmallThreads) {
+      const int row0 = its[k].x;
+      const int row1 = k + 1 < (int)nitems ? its[k + 1].x : N;
+      its[k].y = row1;
+      its[k].w = deg(row0) > kHubThreshold ? -1 : (int)ip[row1];
+    }
+    __syncthreads();
+    const int IP = pow2((int)nitems);
+    for (int k = tid; k < IP; k += kSmallThreads) {
+      uint32_t key = 0xffffffffu;
+      if (k < (int)nitems) key = ((uint32_t)(its[k].w < 0 ? 0 : min(its[k].w - its[k].z, 255)) << 13) | (uint32_t)k;
+      comp[k] = key;
+    }
+    __syncthreads();
+    bitonic_sort_u32(comp, IP);
+    for (int k = tid; k < (int)nitems; k += kSmallThreads)
+      reinterpret_cast<int4*>(items)[k] = its[comp[nitems - 1 - k] & 8191u];
+  }
+  if (tid == 0) counts[2] = (int32_t)nitems;
+}
+
 }  // namespace stag
 extern "C" int64_t stag_csx_items_capacity(int64_t num_edges, int64_t num_nodes);
 namespace stag {
@@ -316,6 +489,22 @@ extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E,
   carve(E, N, (char*)ws, &w);
   const int64_t* key64 = by_dst ? dst : src;
   const int64_t* other64 = by_dst ? src : dst;
+
+  if (E > 0 && N > 0 && E <= kSmallMax && N <= kSmallMax && (!items || stag_csx_items_capacity(E, N) <= 1024)) {
+    // minibatch-sized graph: one launch, one synchronisation
+    const size_t smem = (size_t)(4 * kSmallMax + 4 + 36) * 4 + 1024 * sizeof(int4);
+    static bool attr_set = false;
+    if (!attr_set) {
+      STAG_CUDA(cudaFuncSetAttribute(k_build_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    k_build_small<<<1, kSmallThreads, smem, stream>>>(key64, other64, (int)E, (int)N, indptr, indices, eid, hub_rows,
+                                                      hub_seg_ptr, row_order, items, erow, eidf, (int32_t*)w.totals);
+    STAG_LAUNCH_CHECK();
+    STAG_CUDA(cudaMemcpyAsync(counts_host, w.totals, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    STAG_CUDA(cudaStreamSynchronize(stream));
+    return STAG_OK;
+  }
 
   uint32_t *kin = w.keys_a, *vin = w.vals_a, *kout = w.keys_b, *vout = w.vals_b;
   if (E > 0) {
