@@ -245,19 +245,24 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, in
   rec[j] = make_int4(idx, ef, __float_as_int(a), __float_as_int(b));
 }
 
-// rows without stored edges are not visited by the edge stream: write their zeros
-__global__ void zero_empty_rows_kernel(const AggParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t v = warp; v < p.N; v += nwarps) {
-    if (__ldg(p.indptr + v + 1) != __ldg(p.indptr + v)) continue;
-    for (int s = 0; s < p.S; ++s) {
-      float* o = p.out + (int64_t)s * p.out_ss + v * p.ldo;
-      for (int c = lane; c < p.D; c += 32) o[c] = 0.f;
-      if (p.in_norm && p.norm_scale_out) {  // in-norm factor of a row without edges is 1
-        float* ns = p.norm_scale_out + ((int64_t)s * p.N + v) * p.K;
-        for (int c = lane; c < p.K; c += 32) ns[c] = 1.0f;
+// Rows without stored edges are not visited by the edge stream: every warp of the grid checks 32 rows per load and
+// writes the zeros of the empty ones (rows of the vectorised paths: D % 4 == 0, 16-byte aligned).
+__device__ __forceinline__ void zero_empty_rows_tail(const AggParams& p, int64_t gwarp, int64_t nwarps, int lane) {
+  if (!p.out) return;
+  for (int64_t base = gwarp * 32; base < p.N; base += nwarps * 32) {
+    const int64_t v = base + lane;
+    const bool empty = v < p.N && __ldg(p.indptr + v + 1) == __ldg(p.indptr + v);
+    unsigned m = __ballot_sync(0xffffffffu, empty);
+    while (m) {
+      const int64_t r = base + (__ffs(m) - 1);
+      m &= m - 1;
+      for (int s = 0; s < p.S; ++s) {
+        float* o = p.out + (int64_t)s * p.out_ss + r * p.ldo;
+        for (int c = lane * 4; c < p.D; c += 128) __stcs(reinterpret_cast<float4*>(o + c), make_float4(0.f, 0.f, 0.f, 0.f));
+        if (p.in_norm && p.norm_scale_out) {  // in-norm factor of a row without edges is 1
+          float* ns = p.norm_scale_out + ((int64_t)s * p.N + r) * p.K;
+          for (int c = lane; c < p.K; c += 32) ns[c] = 1.0f;
+        }
       }
     }
   }
@@ -286,8 +291,8 @@ __global__ void zero_empty_rows_kernel(const AggParams p) {
 //   * Box-Muller with sqrt(2 ln 2) folded into B' and the 2^23 magic of the half -> float conversion read
 //     from the constant bank (AggParams::kf): a pair of normals costs PRMT, FFMA, LG2, SQRT | PRMT, FFMA,
 //     FMUL.RZ, COS, SIN | FMUL, 2 FFMA (w) + 2 FFMA (accumulate);
-//   * a row is written (st.global.cs) when the stream passes its last edge; rows without edges are cleared by
-//     zero_empty_rows_kernel; hub segments leave partial sums for hub_finalize_kernel.
+//   * a row is written (st.global.cs) when the stream passes its last edge; rows without edges are cleared in
+//     the kernel's tail (zero_empty_rows_tail); hub segments leave partial sums for hub_finalize_kernel.
 // Where the time goes (B200, arxiv shape, 16 samples): DESIGN.md section 5.
 constexpr int S3_RS = 4;    // data ring slots = edges in flight per lane
 constexpr int S3_NBUF = 4;  // record chunks (of LPR edges) in the record ring
@@ -548,6 +553,9 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
       }
     }
   }
+  // rows without stored edges are not visited by the edge stream: their zeros are written here, by whichever
+  // warps run out of items first
+  zero_empty_rows_tail(p, (int64_t)blockIdx.x * S3_WARPS + warp, total_warps, lane);
 }
 
 // ---- streaming gradient kernel ---------------------------------------------------------------------
@@ -805,6 +813,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
       }
     }
   }
+  zero_empty_rows_tail(p, (int64_t)blockIdx.x * AGG_WARPS + warp, total_warps, lane);
   if (!PG) return;
 
   // ---- parameter-gradient partials: groups of a warp -> warp slice -> CTA row of dp_partial -----------
@@ -1255,10 +1264,19 @@ __global__ void hub_finalize_kernel(const AggParams p, int grads) {
   const int row = p.hub_rows[h];
   const int s0 = p.hub_seg_ptr[h], s1 = p.hub_seg_ptr[h + 1];
   float acc = 0.f, wsum = 0.f;
-  for (int seg = s0; seg < s1; ++seg) {
-    const int64_t o = ((int64_t)s * p.num_hub_segs + seg) * D8 + c;
-    acc += p.part_acc[o];
-    if (!grads && p.in_norm) wsum += p.part_w[o];
+  for (int seg = s0; seg < s1; seg += 8) {  // 8 loads in flight, summed in segment order
+    float v[8], w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t o = ((int64_t)s * p.num_hub_segs + seg + k) * D8 + c;
+      v[k] = seg + k < s1 ? p.part_acc[o] : 0.f;
+      w[k] = (!grads && p.in_norm && seg + k < s1) ? p.part_w[o] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc += v[k];
+      wsum += w[k];
+    }
   }
   if (!grads && p.in_norm) {
     const float indeg = (float)(p.indptr[row + 1] - p.indptr[row]);
@@ -1444,8 +1462,6 @@ static int launch_stream_inst(const AggParams& q, cudaStream_t stream) {
     edge_record_kernel<KIND><<<(unsigned)((q.E + 255) / 256), 256, 0, stream>>>(q, const_cast<int4*>(q.rec), 2);
     STAG_LAUNCH_CHECK();
   }
-  zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(q);
-  STAG_LAUNCH_CHECK();
   STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<KIND, NB, FULL, INNORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
   agg_stream_kernel<KIND, NB, FULL, INNORM><<<grid, S3_THREADS, smem, stream>>>(q);
@@ -1500,8 +1516,6 @@ static int launch_stream2(const AggParams& p_, cudaStream_t stream) {
         p, const_cast<int4*>(p.rec), 1);
     STAG_LAUNCH_CHECK();
   }
-  zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
-  STAG_LAUNCH_CHECK();
   STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<KIND, BODY, false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
   agg_stream_grads_kernel<KIND, BODY, false><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
@@ -1754,10 +1768,6 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
     if (p.E > 0) {
       edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
           p, const_cast<int4*>(p.rec), 1);
-      STAG_LAUNCH_CHECK();
-    }
-    if (dx) {
-      zero_empty_rows_kernel<<<num_sms() * 4, 256, 0, stream>>>(p);
       STAG_LAUNCH_CHECK();
     }
     if (noise->kind == STAG_NOISE_NORMAL) {
