@@ -462,7 +462,9 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
           // groups committed so far: RS + t + j; all but the last RS - 1 are complete, i.e. the row of edge
           // t + j and every record chunk up to the one edge t + j + RS lives in
           cp_async_wait<RS - 1>();
-          __syncwarp();  // records are written by other lanes of the group
+          // records are written by other lanes of the group: a chunk requested at edge t0 has landed in every
+          // lane by edge t0 + RS and is first read at t0 + 2 LPR - RS, so one warp barrier per RS edges orders it
+          if (j == 0) __syncwarp();
           const int4 rc = lds128(rbase + (uint32_t)j * 16u);
           const int ef = rc.y;
           const float A = __int_as_float(rc.z), B = __int_as_float(rc.w);
@@ -731,7 +733,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
 #pragma unroll
       for (int j = 0; j < RS; ++j) {
         cp_async_wait<RS - 1>();
-        __syncwarp();
+        if (j == 0) __syncwarp();  // one warp barrier per RS edges orders the record chunks (see agg_stream_kernel)
         const int4 rc = lds128(rbase + (uint32_t)j * 16u);
         const int ef = rc.y;
         const float A = __int_as_float(rc.z);
