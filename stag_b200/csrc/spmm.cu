@@ -575,15 +575,23 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
 //   PG = false           the two-sum FORWARD for per-channel parameters (or relu): out = P0*a0 + P1'*a1
 //   BODY = 1 (PG false)  per-edge weights (no noise / external [E,1] / generated K == 1 with scalar
 //                        parameters): the lane that loads an edge record computes its weight, out = a0
-// Shared-memory layout per warp: [RS][NQS quads][32 lanes] float4 (NQS = 4 with PG: gathered row + the row's own
-// features), then the record and row rings of the hot kernel; the parameter-gradient staging follows the warps.
-__host__ __device__ constexpr uint32_t s2_warp_bytes(bool pg) { return (uint32_t)(S3_RS * (pg ? 4 : 2) * 512) + S3_REC_BYTES + S3_ROW_BYTES; }
+// Shared-memory layout per warp: [RS][NQS quads][32 lanes] float4 (NQS = 2 NB quads of the gathered row, with PG
+// as many again for the row's own features), then the record and row rings of the hot kernel; the
+// parameter-gradient staging follows the warps.
+// NB = 2 (16 channels per lane) serves scalar parameters and BODY 1 on rows made of 128-channel groups: the
+// parameters and their gradients are then one register each; per-channel parameters keep NB = 1.
+// (with PG and NB = 2 the ring keeps 2 edges in flight instead of 4, so that two CTAs still share an SM)
+__host__ __device__ constexpr int s2_ring_slots(bool pg, int nb) { return (pg && nb == 2) ? 2 : S3_RS; }
+__host__ __device__ constexpr uint32_t s2_warp_bytes(bool pg, int nb) {
+  return (uint32_t)(s2_ring_slots(pg, nb) * (pg ? 4 : 2) * nb * 512) + S3_REC_BYTES + S3_ROW_BYTES;
+}
 
-template <int KIND, int BODY, bool PG>
+template <int KIND, int BODY, bool PG, int NB>
 __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const AggParams p) {
   extern __shared__ float4 ring[];
-  constexpr int RS = S3_RS, NQS = PG ? 4 : 2;
-  constexpr uint32_t SLOT = NQS * 512u, DATA_BYTES = RS * SLOT, WARP_BYTES = s2_warp_bytes(PG);
+  constexpr int RS = s2_ring_slots(PG, NB), NQ = 2 * NB, NA = 4 * NQ, GW = 64 * NB, NQS = PG ? 2 * NQ : NQ;
+  constexpr int NP = NB == 1 ? 8 : 1;  // parameter (gradient) registers: per channel, or one scalar
+  constexpr uint32_t SLOT = NQS * 512u, DATA_BYTES = RS * SLOT, WARP_BYTES = s2_warp_bytes(PG, NB);
   constexpr float kRad = 1.1774100225154747f;  // sqrt(2 ln 2): the radius is taken as sqrt(-lg2 u1)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -605,17 +613,18 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
   const int64_t total = (int64_t)IG * p.S;
   const int64_t total_warps = (int64_t)gridDim.x * AGG_WARPS;
 
-  // this lane's channels (single chunk: dpad <= LPR * 8) and parameters; Normal: P1 carries sqrt(2 ln 2)
-  const int c = first_chan(0, sl);
-  const bool qvalid = c < p.D;
-  const bool qvalid2 = c + 32 < p.D;
-  const uint32_t blk = (uint32_t)sl;
-  float P0[8], P1[8], d0[8], d1[8];
+  // this lane's channels (single pass: dpad <= LPR * 8 NB): quads at c + 32 j; element i is channel
+  // c + 32 (i / 4) + i % 4.  Normal: P1 carries sqrt(2 ln 2)
+  const int c = (sl >> 3) * GW + ((sl & 7) << 2);
+  bool qv[NQ];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int ch = chan(c, i);
-    const bool ok = ch < p.D;
-    const int64_t pi = p.pshape == STAG_PARAM_SCALAR ? 0 : (ok ? ch : 0);
+  for (int j = 0; j < NQ; ++j) qv[j] = c + 32 * j < p.D;
+  const uint32_t blk0 = (uint32_t)((sl >> 3) * 8 * NB + (sl & 7));  // Philox blocks blk0 + 8 g
+  float P0[NP], P1[NP], d0[NP], d1[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int ch = c + 32 * (i >> 2) + (i & 3);
+    const int64_t pi = (NB == 2 || p.pshape == STAG_PARAM_SCALAR) ? 0 : (ch < p.D ? ch : 0);
     P0[i] = BODY == 0 ? __ldg(p.p0 + pi) : 1.0f;
     P1[i] = BODY == 0 ? __ldg(p.p1 + pi) : 0.0f;
     if (BODY == 0 && KIND == STAG_NOISE_UNIFORM) P1[i] -= P0[i];  // w = low + u * (high - low)
@@ -650,15 +659,15 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
 
-    const char* gsb = reinterpret_cast<const char*>(p.x + (int64_t)s * p.x_ss + (qvalid ? c : 0));  // gathered operand
-    const char* xrb = PG ? reinterpret_cast<const char*>(p.xrow + (int64_t)s * p.xr_ss + (qvalid ? c : 0)) : nullptr;
+    const char* gsb = reinterpret_cast<const char*>(p.x + (int64_t)s * p.x_ss + (qv[0] ? c : 0));  // gathered operand
+    const char* xrb = PG ? reinterpret_cast<const char*>(p.xrow + (int64_t)s * p.xr_ss + (qv[0] ? c : 0)) : nullptr;
     float* outs = p.out ? p.out + (int64_t)s * p.out_ss : nullptr;
     const uint32_t smp = (uint32_t)(p.sample_base + s);
     const int4* recp = p.rec + e0;
     const int32_t* rowp = p.erow + e0;
-    float a0[8], a1[8];
+    float a0[NA], a1[NA];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+    for (int i = 0; i < NA; ++i) a0[i] = a1[i] = 0.f;
 
     // records {neighbour, eid | last << 31, A, -} and rows -> rings (zeros past the end of the item)
     auto fetch_chunk = [&](int first) {
@@ -691,17 +700,36 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
       if (PG) {
         const int4 r = lds128(rec_addr);
         const char* src = gsb + (uint64_t)(uint32_t)r.x * ldxb;
-        cp_async16(dst, src, off || !qvalid);
-        cp_async16(dst + 512u, src + 128, off || !qvalid2);
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) cp_async16(dst + (uint32_t)j * 512u, src + 128 * j, off || !qv[j]);
         if (r.y < 0 && e < rowlim) {  // the row ends with this edge: fetch its own feature row as well
           const char* xs = xrb + (uint64_t)(uint32_t)lds32(row_addr) * ldxrb;
-          cp_async16(dst + 1024u, xs, !qvalid);
-          cp_async16(dst + 1536u, xs + 128, !qvalid2);
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) cp_async16(dst + (uint32_t)(NQ + j) * 512u, xs + 128 * j, !qv[j]);
         }
       } else {
         const char* src = gsb + (uint64_t)(uint32_t)lds32(rec_addr) * ldxb;
-        cp_async16(dst, src, off || !qvalid);
-        cp_async16(dst + 512u, src + 128, off || !qvalid2);
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) cp_async16(dst + (uint32_t)j * 512u, src + 128 * j, off || !qv[j]);
+      }
+    };
+    auto put_row = [&](float* rowq, int width, const float* v, bool streaming) {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j)
+        if (c + 32 * j < width && qv[j]) {
+          const float4 q4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (streaming) __stcs(reinterpret_cast<float4*>(rowq + c + 32 * j), q4);
+          else *reinterpret_cast<float4*>(rowq + c + 32 * j) = q4;
+        }
+    };
+    // parameter gradients of a finished row (or hub segment) against the row's own features xr
+    auto add_param_grads = [&](const float* xr) {
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        const int k = NB == 1 ? i : 0;
+        const float t1 = xr[i] * a1[i];
+        d1[k] += t1;
+        d0[k] += KIND == STAG_NOISE_NORMAL ? xr[i] * a0[i] : xr[i] * a0[i] - t1;
       }
     };
 
@@ -738,56 +766,63 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
         const int ef = rc.y;
         const float A = __int_as_float(rc.z);
         const uint32_t slot_s = data_s + (uint32_t)j * SLOT;
-        float raw[8];
+        float raw[NA];
         if (BODY == 0) {
-          const uint4 r4 = philox_rk(blk, (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
-          const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float xl = __uint_as_float(__byte_perm(q[i], kf, 0x7610));
-            const float xh = __uint_as_float(__byte_perm(q[i], kf, 0x7632));
-            if (KIND == STAG_NOISE_NORMAL) {  // eps / sqrt(2 ln 2)
-              const float rad = mufu_sqrt(-mufu_lg2(fmaf(xl, 1.52587890625e-05f, -127.99999237060547f)));
-              const float ang = fmaf(xh, 9.58738019107841e-05f, -804.2476806640625f);
-              raw[2 * i] = rad * mufu_cos(ang);
-              raw[2 * i + 1] = rad * mufu_sin(ang);
-            } else {
-              raw[2 * i] = fmaf(xl, 1.52587890625e-05f, -128.0f);
-              raw[2 * i + 1] = fmaf(xh, 1.52587890625e-05f, -128.0f);
+          for (int g = 0; g < NB; ++g) {
+            const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
+            const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float xl = __uint_as_float(__byte_perm(q[i], kf, 0x7610));
+              const float xh = __uint_as_float(__byte_perm(q[i], kf, 0x7632));
+              if (KIND == STAG_NOISE_NORMAL) {  // eps / sqrt(2 ln 2)
+                const float rad = mufu_sqrt(-mufu_lg2(fmaf(xl, 1.52587890625e-05f, -127.99999237060547f)));
+                const float ang = fmaf(xh, 9.58738019107841e-05f, -804.2476806640625f);
+                raw[8 * g + 2 * i] = rad * mufu_cos(ang);
+                raw[8 * g + 2 * i + 1] = rad * mufu_sin(ang);
+              } else {
+                raw[8 * g + 2 * i] = fmaf(xl, 1.52587890625e-05f, -128.0f);
+                raw[8 * g + 2 * i + 1] = fmaf(xh, 1.52587890625e-05f, -128.0f);
+              }
             }
           }
         }
-        const float4 xa = lds128f(slot_s), xb = lds128f(slot_s + 512u);
-        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        float xv[NA];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int jq = 0; jq < NQ; ++jq) {
+          const float4 x4 = lds128f(slot_s + (uint32_t)jq * 512u);
+          xv[4 * jq] = x4.x; xv[4 * jq + 1] = x4.y; xv[4 * jq + 2] = x4.z; xv[4 * jq + 3] = x4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
           if (BODY == 1) {
             a0[i] = fmaf(A, xv[i], a0[i]);
           } else {
             float y = A * xv[i];
-            if (p.relu && !(fmaf(raw[i], P1[i], P0[i]) > 0.f)) y = 0.f;
+            if (p.relu && !(fmaf(raw[i], P1[NB == 1 ? i : 0], P0[NB == 1 ? i : 0]) > 0.f)) y = 0.f;
             a0[i] += y;
             a1[i] = fmaf(raw[i], y, a1[i]);
           }
         }
         if (ef < 0 && t + j < rowlim) {  // end of a row: group-uniform
           const int rw = lds32(wbase + (uint32_t)j * 4u);
-          float dxv[8];
+          float dxv[NA];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dxv[i] = BODY == 1 ? a0[i] : fmaf(P1[i], a1[i], P0[i] * a0[i]);
-          if (outs && qvalid) store8<true, true>(outs + (int64_t)rw * p.ldo, c, p.D, dxv);
+          for (int i = 0; i < NA; ++i)
+            dxv[i] = BODY == 1 ? a0[i] : fmaf(P1[NB == 1 ? i : 0], a1[i], P0[NB == 1 ? i : 0] * a0[i]);
+          if (outs) put_row(outs + (int64_t)rw * p.ldo, p.D, dxv, true);
           if (PG) {
-            const float4 ra = lds128f(slot_s + 1024u), rb = lds128f(slot_s + 1536u);
-            const float xr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+            float xr[NA];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float t1 = xr[i] * a1[i];
-              d1[i] += t1;
-              d0[i] += KIND == STAG_NOISE_NORMAL ? xr[i] * a0[i] : xr[i] * a0[i] - t1;
+            for (int jq = 0; jq < NQ; ++jq) {
+              const float4 r4 = lds128f(slot_s + (uint32_t)(NQ + jq) * 512u);
+              xr[4 * jq] = r4.x; xr[4 * jq + 1] = r4.y; xr[4 * jq + 2] = r4.z; xr[4 * jq + 3] = r4.w;
             }
+            add_param_grads(xr);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+          for (int i = 0; i < NA; ++i) a0[i] = a1[i] = 0.f;
         }
         issue(t + j + RS, ibase + (uint32_t)j * 16u, vbase + (uint32_t)j * 4u, j);
         cp_async_commit();
@@ -798,20 +833,24 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
     if (part_slot >= 0) {
       // hub segment: partial sums (row scale applied by hub_finalize_kernel); parameter gradients against the
       // hub row's own features, scaled here
-      float dxv[8];
+      if (outs) {
+        float dxv[NA];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dxv[i] = BODY == 1 ? a0[i] : fmaf(P1[i], a1[i], P0[i] * a0[i]);
-      if (outs && qvalid) store8<true, false>(p.part_acc + ((int64_t)s * p.num_hub_segs + part_slot) * D8, c, D8, dxv);
+        for (int i = 0; i < NA; ++i)
+          dxv[i] = BODY == 1 ? a0[i] : fmaf(P1[NB == 1 ? i : 0], a1[i], P0[NB == 1 ? i : 0] * a0[i]);
+        put_row(p.part_acc + ((int64_t)s * p.num_hub_segs + part_slot) * D8, D8, dxv, false);
+      }
       if (PG && nedges > 0) {
-        float xr[8];
-        load8<true>(p.xrow + (int64_t)s * p.xr_ss + (int64_t)hub_row * p.ldxr, c, p.D, xr);
+        const float* xrow = p.xrow + (int64_t)s * p.xr_ss + (int64_t)hub_row * p.ldxr;
         const float rs = p.rscale ? __ldg(p.rscale + hub_row) : 1.0f;
+        float xr[NA];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xs = xr[i] * rs, t1 = xs * a1[i];
-          d1[i] += t1;
-          d0[i] += KIND == STAG_NOISE_NORMAL ? xs * a0[i] : xs * a0[i] - t1;
+        for (int jq = 0; jq < NQ; ++jq) {
+          float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (qv[jq]) r4 = __ldg(reinterpret_cast<const float4*>(xrow + c + 32 * jq));
+          xr[4 * jq] = r4.x * rs; xr[4 * jq + 1] = r4.y * rs; xr[4 * jq + 2] = r4.z * rs; xr[4 * jq + 3] = r4.w * rs;
         }
+        add_param_grads(xr);
       }
     }
   }
@@ -819,13 +858,14 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
   if (!PG) return;
 
   // ---- parameter-gradient partials: groups of a warp -> warp slice -> CTA row of dp_partial -----------
+  // (scalar parameters with NB = 2: the lane's single partial sits at its first channel, the finalize sums all)
   if (KIND == STAG_NOISE_NORMAL) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d1[i] *= kRad;  // a1 was accumulated against eps / sqrt(2 ln 2)
+    for (int i = 0; i < NP; ++i) d1[i] *= kRad;  // a1 was accumulated against eps / sqrt(2 ln 2)
   }
   for (int o = LPR; o < 32; o <<= 1) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NP; ++i) {
       d0[i] += __shfl_xor_sync(0xffffffffu, d0[i], o);
       d1[i] += __shfl_xor_sync(0xffffffffu, d1[i], o);
     }
@@ -835,10 +875,11 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
   __syncwarp();
   if (sub == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (chan(c, i) < D8) {
-        my_stage[chan(c, i)] = d0[i];
-        my_stage[D8 + chan(c, i)] = d1[i];
+    for (int i = 0; i < NP; ++i) {
+      const int ch = c + 32 * (i >> 2) + (i & 3);
+      if (ch < D8) {
+        my_stage[ch] = d0[i];
+        my_stage[D8 + ch] = d1[i];
       }
     }
   }
@@ -1504,25 +1545,40 @@ static int launch_psh(int psh, const AggParams& p, bool vec, int grid, size_t sm
 }
 
 // forward (or dX-only) launches of the two-sum / per-edge-weight streaming kernel
-template <int KIND, int BODY>
-static int launch_stream2(const AggParams& p_, cudaStream_t stream) {
-  AggParams p = p_;
-  if (p.lpr_log2 < 3) p.lpr_log2 = 3;  // record chunks of at least 8 edges (narrow rows leave lanes idle)
+template <int KIND, int BODY, int NB>
+static int launch_stream2_inst(const AggParams& p, cudaStream_t stream) {
   const int RPW = 32 >> p.lpr_log2;
   const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S;
   const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
   const int sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * 2 ? ctas : num_sms() * 2));
-  const size_t ring_bytes = (size_t)AGG_WARPS * s2_warp_bytes(false);
+  const size_t ring_bytes = (size_t)AGG_WARPS * s2_warp_bytes(false, NB);
   if (p.E > 0) {
     edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
         p, const_cast<int4*>(p.rec), 1);
     STAG_LAUNCH_CHECK();
   }
-  STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<KIND, BODY, false>,
+  STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<KIND, BODY, false, NB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-  agg_stream_grads_kernel<KIND, BODY, false><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+  agg_stream_grads_kernel<KIND, BODY, false, NB><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
   STAG_LAUNCH_CHECK();
   return STAG_OK;
+}
+
+// lanes per row of the two-sum kernel: NB = 2 (16 channels per lane) for scalar parameters / per-edge weights on
+// rows made of 128-channel groups, else NB = 1; record chunks of at least 8 edges (narrow rows leave lanes idle)
+static int two_sum_blocks_per_lane(AggParams& p, bool scalar_params) {
+  const int nb = (scalar_params && p.dpad % 128 == 0) ? 2 : 1;
+  p.lpr_log2 = lpr_log2_for((blocks_for(p.D) + nb - 1) / nb);
+  if (p.lpr_log2 < 3) p.lpr_log2 = 3;
+  return nb;
+}
+
+// forward (or dX-only) launches of the two-sum / per-edge-weight streaming kernel
+template <int KIND, int BODY>
+static int launch_stream2(const AggParams& p_, cudaStream_t stream) {
+  AggParams p = p_;
+  const int nb = two_sum_blocks_per_lane(p, BODY == 1 || p.pshape == STAG_PARAM_SCALAR);
+  return nb == 2 ? launch_stream2_inst<KIND, BODY, 2>(p, stream) : launch_stream2_inst<KIND, BODY, 1>(p, stream);
 }
 
 template <bool GRADS>
@@ -1761,26 +1817,30 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   int sgrid = grid;
   if (stream_ok) {
     p.rec = (const int4*)((char*)ws + L.rec);
-    if (p.lpr_log2 < 3) p.lpr_log2 = 3;  // record chunks of at least 8 edges
+    const int nb = two_sum_blocks_per_lane(p, p.pshape == STAG_PARAM_SCALAR);
     const int RPW = 32 >> p.lpr_log2;
     const int64_t warp_items = (int64_t)((p.num_hub_segs + p.num_items + RPW - 1) / RPW) * p.S;
     const int64_t ctas = (warp_items + AGG_WARPS - 1) / AGG_WARPS;
     sgrid = (int)(ctas < 1 ? 1 : (ctas < num_sms() * 2 ? ctas : num_sms() * 2));
-    const size_t ring_bytes = (size_t)AGG_WARPS * s2_warp_bytes(true) + smem;
+    const size_t ring_bytes = (size_t)AGG_WARPS * s2_warp_bytes(true, nb) + smem;
     if (p.E > 0) {
       edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(
           p, const_cast<int4*>(p.rec), 1);
       STAG_LAUNCH_CHECK();
     }
-    if (noise->kind == STAG_NOISE_NORMAL) {
-      STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<STAG_NOISE_NORMAL, 0, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-      agg_stream_grads_kernel<STAG_NOISE_NORMAL, 0, true><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
-    } else {
-      STAG_CUDA(cudaFuncSetAttribute(agg_stream_grads_kernel<STAG_NOISE_UNIFORM, 0, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
-      agg_stream_grads_kernel<STAG_NOISE_UNIFORM, 0, true><<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
-    }
+    auto launch = [&](auto kern) -> int {
+      STAG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+      kern<<<sgrid, AGG_THREADS, ring_bytes, stream>>>(p);
+      return STAG_OK;
+    };
+    int lrc;
+    if (noise->kind == STAG_NOISE_NORMAL)
+      lrc = nb == 2 ? launch(agg_stream_grads_kernel<STAG_NOISE_NORMAL, 0, true, 2>)
+                    : launch(agg_stream_grads_kernel<STAG_NOISE_NORMAL, 0, true, 1>);
+    else
+      lrc = nb == 2 ? launch(agg_stream_grads_kernel<STAG_NOISE_UNIFORM, 0, true, 2>)
+                    : launch(agg_stream_grads_kernel<STAG_NOISE_UNIFORM, 0, true, 1>);
+    if (lrc) return lrc;
     STAG_LAUNCH_CHECK();
   } else {
     rc = launch_agg<true>(p, vec, grid, smem, stream);
