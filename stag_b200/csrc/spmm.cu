@@ -14,21 +14,21 @@
 //   degree scalings                stag/zoo/gcn.py:67-75,100-108
 //   autograd of the above          DGL GSpMM.backward (gspmm on the reverse graph + gsddmm)
 //
-// Mapping: a row (destination node for CSC, source node for CSR) is owned by a group of LPR
-// lanes; each lane owns one OCT of channels (8 floats = two 128-bit loads = one Philox block
-// per edge).  D = 128 -> LPR = 16, two rows per warp; narrower rows pack more rows per warp,
-// wider rows loop over channel chunks.  The group first loads up to LPR edge records
-// (neighbour id, edge id, gather scale, and for per-edge noise the weight itself) with one
-// coalesced load per lane and then broadcasts them edge by edge with shuffles.
-// Rows longer than kHubThreshold are cut into segments that are scheduled as independent
-// work items and combined in a fixed order by a finalize kernel (deterministic).
-//
-// MODE 0  per-edge scalar weight (none / external [E,1] / generated K == 1): folded into the
-//         broadcast scale, the inner loop is 2 x LDG.128 + 8 FFMA
-// MODE 1  external per-channel weights [E,K] read from memory (the shared-noise parity seam)
-// MODE 2  per-channel noise generated in registers; PSH 0: scalar or per-edge parameters
-//         (travel with the edge record, folded with the gather scale), 1: per-channel
-//         parameters in registers, 2: per-edge-per-channel parameters read from memory
+// Three kernel families share one edge schedule (StagGraph: stream items = consecutive rows holding about 64
+// stored edges, rows longer than kHubThreshold cut into segments combined in a fixed order by a finalize
+// kernel: deterministic):
+//   agg_stream_kernel        the hot one: generated per-channel noise (or none) with scalar / per-edge
+//                            parameters, forward and transposed pass; 16 channels per lane
+//   agg_stream_grads_kernel  the two-sum form: parameter gradients (vi=True), per-channel parameters, relu,
+//                            per-edge weights
+//   agg_kernel               row per lane group, the general fallback:
+//     MODE 0  per-edge scalar weight (none / external [E,1] / generated K == 1)
+//     MODE 1  external per-channel weights [E,K] read from memory (the shared-noise parity seam)
+//     MODE 2  per-channel noise generated in registers; PSH 0: scalar or per-edge parameters
+//             (travel with the edge record, folded with the gather scale), 1: per-channel
+//             parameters in registers, 2: per-edge-per-channel parameters read from memory
+// A row (destination node for CSC, source node for CSR) is owned by a group of LPR lanes; a lane owns one or
+// two OCTs of channels (8 floats = two 128-bit loads = one Philox block per edge).
 #include <stdlib.h>
 #include "common.cuh"
 #include "noise.cuh"
@@ -167,15 +167,6 @@ __device__ __forceinline__ void folded_oct(uint32_t eid, uint32_t oct, uint32_t 
 }
 
 // ---- shared pieces of the streaming kernels -------------------------------------------------------------
-#ifndef STAG_RING_STAGES
-#define STAG_RING_STAGES 4
-#endif
-constexpr int RING_STAGES = STAG_RING_STAGES;
-// next ring stage (a mask when the stage count is a power of two)
-__device__ __forceinline__ int ring_next(int i) {
-  return (RING_STAGES & (RING_STAGES - 1)) == 0 ? ((i + 1) & (RING_STAGES - 1)) : (i + 1 == RING_STAGES ? 0 : i + 1);
-}  // edges per ring stage, computed as independent chains
-
 // 16-byte async copy global -> shared; `ignore` set: the source is not read and zeros are written
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool ignore) {
   asm volatile(
