@@ -60,10 +60,25 @@ def check(src, dst, n, lib):
 
 
 @pytest.mark.parametrize("n,e", [(1, 0), (1, 7), (5, 0), (3, 9), (50, 300), (257, 4096), (1000, 4097),
+                                 (8192, 8192), (8191, 8000), (40, 8192), (8193, 8192), (8192, 8193),
                                  (70000, 300000), (169343, 1166243)])
 def test_csx_random(n, e, lib):
     rng = np.random.default_rng(n * 31 + e)
     check(rng.integers(0, n, e), rng.integers(0, n, e), n, lib)
+
+
+def test_csx_minibatch_of_molecules(lib):
+    """A block-diagonal batch of molecule-sized graphs (the single-launch shared-memory builder)."""
+    rng = np.random.default_rng(11)
+    src, dst, off = [], [], 0
+    for _ in range(128):
+        n = int(np.clip(rng.normal(25.5, 12), 2, 80))
+        e = max(1, int(1.1 * n))
+        s, d = rng.integers(0, n, e), rng.integers(0, n, e)
+        src += [s + off, d + off]
+        dst += [d + off, s + off]
+        off += n
+    check(np.concatenate(src), np.concatenate(dst), off, lib)
 
 
 def test_csx_powerlaw_hubs(lib):
