@@ -155,12 +155,14 @@ def run_reference(args, rank):
 class Path:
     """The hot path at the C ABI: pre-built CSC/CSR, resident buffers, direct ctypes calls."""
 
-    def __init__(self, dev, src, dst, S, sample_base, vi):
+    def __init__(self, dev, src, dst, S, sample_base, vi, normal="hadamard"):
         import torch
         import stag_b200 as sb
         from stag_b200 import _lib
         self.torch, self._lib, self.lib = torch, _lib, _lib.load()
         self.dev, self.S, self.vi, self.sample_base = dev, S, vi, sample_base
+        # vi = True needs d loc / d scale: the two-sum kernel, Box-Muller normals
+        self.normal_kind = _lib.NOISE_NORMAL_HADAMARD if (normal == "hadamard" and not vi) else _lib.NOISE_NORMAL
         self.g = sb.Graph(torch.from_numpy(src), torch.from_numpy(dst), N_NODES).to(dev)
         st = self.g._s
         self.csc, self.csc_keep = st.csx(True)
@@ -186,7 +188,7 @@ class Path:
 
     def noise(self, layer):
         n = self._lib.StagNoise()
-        n.kind, n.K, n.param_shape = self._lib.NOISE_NORMAL, WIDTH, self._lib.PARAM_SCALAR
+        n.kind, n.K, n.param_shape = self.normal_kind, WIDTH, self._lib.PARAM_SCALAR
         n.relu = n.in_norm = 0
         n.sample_base = self.sample_base
         n.p0, n.p1, n.external = self.loc.data_ptr(), self.scale.data_ptr(), 0
@@ -242,7 +244,7 @@ class Path:
         self.offset += N_LAYERS
 
 
-def e2e_leg(dev, src, dst, S, sample_base, steps, warmup, dist):
+def e2e_leg(dev, src, dst, S, sample_base, steps, warmup, dist, normal="hadamard"):
     """Same metric through the public Python API (stag_b200.ops.stochastic_aggregate + autograd)
     with HOST buffers: every step copies X [N,D] from pinned host memory, runs the 3-layer
     forward and backward, and reads dX [N,D] and the scalar objective back to the host."""
@@ -288,7 +290,7 @@ def e2e_leg(dev, src, dst, S, sample_base, steps, warmup, dist):
         h = x
         for layer in range(N_LAYERS):
             spec = sb.ops.NoiseSpec("normal", loc, scale, WIDTH, N_EDGES, n_samples=S, sample_base=sample_base,
-                                    batched=True)
+                                    batched=True, generator=normal)
             h = sb.ops.stochastic_aggregate(g, h, spec, src_scale=ss, dst_scale=ds, n_samples=S)
         obj = h.mean()
         obj.backward()
@@ -354,7 +356,7 @@ def run_ours(args, rank, world):
     S = N_SAMPLES
     vi = args.mode == "vi"
     src, dst = synth_graph()
-    path = Path(dev, src, dst, S, sample_base=rank * S, vi=vi)
+    path = Path(dev, src, dst, S, sample_base=rank * S, vi=vi, normal=args.normal)
     for _ in range(max(args.warmup, 3)):
         path.step()
     torch.cuda.synchronize()
@@ -397,7 +399,8 @@ def run_ours(args, rank, world):
     peak, peak_src = peaks()
     achieved = alg / (avg_ms * 1e-3) / 1e9
     step_bytes = bytes_fwd(S, True) + 2 * bytes_fwd(S, False) + 2 * bytes_bwd(S, vi, False) + bytes_bwd(S, vi, True)
-    roof = {"bound": "hbm", "kernel": "stag::agg_stream_kernel<NORMAL, 2 blocks per lane> (%s launches)" % dom, "achieved": achieved, "peak": peak,
+    roof = {"bound": "hbm", "kernel": ("stag::agg_tc_kernel (%s launches)" if path.normal_kind == path._lib.NOISE_NORMAL_HADAMARD
+                       else "stag::agg_stream_kernel<NORMAL, 2 blocks per lane> (%s launches)") % dom, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
             "share_of_step": tot[dom] / sum(tot.values()),
@@ -408,7 +411,7 @@ def run_ours(args, rank, world):
         with open(prof) as f:
             roof["traffic"] = json.load(f).get(dom)
 
-    e2e_s, h2d, d2h = e2e_leg(dev, src, dst, S, rank * S, max(3, min(args.steps, 8)), 5, dist)
+    e2e_s, h2d, d2h = e2e_leg(dev, src, dst, S, rank * S, max(3, min(args.steps, 8)), 5, dist, args.normal)
     e2e = {"value": edge_samples / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "api": "stag_b200.ops.stochastic_aggregate + autograd, pinned host X in / dX + objective out every step, copies double-buffered on two copy streams"}
     if rank != 0:
@@ -418,6 +421,8 @@ def run_ours(args, rank, world):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "mode": args.mode, "layers": N_LAYERS, "mc_samples_per_gpu": S,
+                       "normal_generator": ("hadamard (tensor cores)" if path.normal_kind == path._lib.NOISE_NORMAL_HADAMARD
+                                            else "boxmuller (16-bit halves)"),
                        "sharded_unit": "MC samples (Philox sample index), no data-path collective",
                        "l2": "per-launch inputs (1.39 GB activations per layer) exceed the 126 MB L2; "
                              "layer-1 X (87 MB) is deliberately L2-resident across its 16 samples"},
@@ -433,6 +438,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="mle", choices=["mle", "vi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--normal", default="boxmuller", choices=["hadamard", "boxmuller"],
+                    help="standard-normal generator of the fused kernels: tensor-core Walsh-Hadamard mix "
+                         "(agg_tc_kernel) or 16-bit Box-Muller (agg_stream_kernel)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -58,7 +58,12 @@ enum {
   STAG_NOISE_EXTERNAL = 1,  /* w read from a caller tensor [S,E,K] in ORIGINAL edge order (parity seam) */
   STAG_NOISE_NORMAL = 2,    /* w = loc + scale*eps            torch/distributions/normal.py:82-85   */
   STAG_NOISE_UNIFORM = 3,   /* w = low + u*(high-low)         torch/distributions/uniform.py:85-88  */
-  STAG_NOISE_BERNOULLI = 4  /* w = (u < probs)                torch/distributions/bernoulli.py:116-119 */
+  STAG_NOISE_BERNOULLI = 4, /* w = (u < probs)                torch/distributions/bernoulli.py:116-119 */
+  /* w = loc + scale*eps like STAG_NOISE_NORMAL, with eps drawn by the tensor-core generator: the 128 channels of
+   * a group are the Walsh-Hadamard mix of 128 masked random FP8 bytes (csrc/spmm_tc.cuh; normal to 5.6e-6 in
+   * Kolmogorov distance).  A different stream than STAG_NOISE_NORMAL.  Fused path: K == D, D % 128 == 0, scalar
+   * or per-edge parameters, no relu / in_norm / parameter gradients; stag_noise_emit: K % 128 == 0. */
+  STAG_NOISE_NORMAL_HADAMARD = 5
 };
 
 /* shape class of the distribution parameters before `expand([E,K])` (stag/layers.py:117-119) */

@@ -120,11 +120,59 @@ def std_normal(num_edges, K, sample, seed, offset):
     return _to_channels(z.astype(np.float32), K)
 
 
+# ---- STAG_NOISE_NORMAL_HADAMARD (stag_b200/csrc/spmm_tc.cuh, noise.cuh wh_*) ---------------------------------
+# byte k (0..127) of an (edge, sample, 128-channel group g) = byte k % 16 (little endian) of Philox block
+# 8 g + k // 16; FP8 e4m3 code = (byte & 0xCD) | 0x12; z[c] = WH_INV_SD * sum_k (-1)^popcount(c & k) value(code_k).
+WH_AND, WH_OR = 0xCD, 0x12
+WH_INV_SD = np.float32(0.006240209594902129)   # 1 / sqrt(128 * 105186885 / 524288)
+
+
+def e4m3_value(code):
+    """Value of an e4m3 code (normal numbers; the masked codes never are subnormal or NaN)."""
+    code = np.asarray(code, dtype=np.int64)
+    sign = np.where(code & 0x80, -1.0, 1.0)
+    e = (code >> 3) & 0xF
+    m = code & 7
+    return sign * (1.0 + m / 8.0) * np.exp2(e - 7.0)
+
+
+def hadamard_matrix(n=128):
+    k = np.arange(n)
+    par = np.zeros((n, n), dtype=np.int64)
+    x = k[:, None] & k[None, :]
+    while x.any():
+        par ^= x & 1
+        x >>= 1
+    return 1.0 - 2.0 * par
+
+
+def hadamard_sums(num_edges, K, sample, seed, offset):
+    """float64 [E, K] raw sums (exact: multiples of 2^-8 below 2^12), original edge order."""
+    assert K % 128 == 0
+    G = K // 128
+    eid = np.arange(num_edges, dtype=np.uint32)[:, None]
+    blk = np.arange(8 * G, dtype=np.uint32)[None, :]
+    r = np.stack(raw_block(eid, blk, np.uint32(sample), seed, offset), axis=-1)          # [E, 8G, 4] words
+    by = np.stack([(r >> np.uint32(8 * b)) & np.uint32(0xFF) for b in range(4)], axis=-1)  # [E, 8G, 4, 4]
+    code = (by.reshape(num_edges, G, 128).astype(np.int64) & WH_AND) | WH_OR
+    v = e4m3_value(code)                                                                  # [E, G, 128]
+    return (v @ hadamard_matrix().T).reshape(num_edges, K)
+
+
+def hadamard_normal(num_edges, K, sample, seed, offset):
+    return (hadamard_sums(num_edges, K, sample, seed, offset).astype(np.float32) * WH_INV_SD).astype(np.float32)
+
+
 def noise(kind, num_edges, K, sample, seed, offset, p0=None, p1=None, relu=False):
     """w [E,K] float32 for a distribution kind in {'normal','uniform','bernoulli'};
     p0/p1 broadcastable to [E,K] (loc/scale, low/high, probs)."""
     if kind == "normal":
         w = np.float32(p0) + std_normal(num_edges, K, sample, seed, offset) * np.float32(p1)
+    elif kind == "normal_hadamard":
+        # the kernels evaluate fma(sum, scale * WH_INV_SD, loc) in fp32
+        b = (np.asarray(p1, dtype=np.float32) * WH_INV_SD).astype(np.float32)
+        w = (hadamard_sums(num_edges, K, sample, seed, offset) * b.astype(np.float64)
+             + np.asarray(p0, dtype=np.float32).astype(np.float64)).astype(np.float32)
     elif kind == "uniform":
         w = np.float32(p0) + uniform(num_edges, K, sample, seed, offset) * (np.float32(p1) - np.float32(p0))
     elif kind == "bernoulli":

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "_C", "libstag_b200.so")
 
 STAG_OK, STAG_EINVAL, STAG_ECUDA, STAG_EWORKSPACE, STAG_EUNSUPPORTED = 0, -1, -2, -3, -4
 NOISE_NONE, NOISE_EXTERNAL, NOISE_NORMAL, NOISE_UNIFORM, NOISE_BERNOULLI = 0, 1, 2, 3, 4
+NOISE_NORMAL_HADAMARD = 5
 PARAM_SCALAR, PARAM_CHANNEL, PARAM_EDGE, PARAM_EDGE_CHANNEL = 0, 1, 2, 3
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)

@@ -50,6 +50,8 @@ struct AggParams {
   const int32_t* erow;       // row of every stored edge
   const int32_t* eidf;       // edge id of every stored edge, bit 31 set on the last edge of its row
   const int4* rec;           // per-call edge records (edge_record_kernel), workspace
+  const int32_t* ebnd;       // tensor-core path: edge boundaries of the units (tc_bounds_kernel), workspace
+  int nunits;
   int num_items;
   uint32_t rk[2 * kPhiloxRounds];  // Philox round keys
   uint32_t kf;                     // 0x4B000000 (2^23 as float bits), read from the constant bank by PRMT
@@ -1410,6 +1412,47 @@ __global__ void segment_reduce_kernel(const float* __restrict__ feat, int64_t ld
   out[(int64_t)b * ldo + c] = acc;
 }
 
+// noise materialisation of STAG_NOISE_NORMAL_HADAMARD: one warp per (sample, edge, 128-channel group)
+__global__ void emit_wh_kernel(const AggParams p, float* __restrict__ w_out, float* __restrict__ eps_out) {
+  const int lane = threadIdx.x & 31;
+  const int G = p.K >> 7;
+  const int64_t total = (int64_t)p.S * p.E * G;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += nwarps) {
+    const int g = (int)(i % G);
+    const int64_t e = (i / G) % p.E;
+    const int s = (int)(i / ((int64_t)G * p.E));
+    float v[4];
+    wh_group_sums((uint32_t)e, (uint32_t)g, (uint32_t)(p.sample_base + s), p.key, lane, v);
+    const int ch = 128 * g + 4 * lane;
+    float w[4], z[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int64_t pi;
+      switch (p.pshape) {
+        case STAG_PARAM_SCALAR: pi = 0; break;
+        case STAG_PARAM_CHANNEL: pi = ch + b; break;
+        case STAG_PARAM_EDGE: pi = e; break;
+        default: pi = e * p.K + ch + b; break;
+      }
+      z[b] = v[b] * kWhInvSd;
+      // the fused kernel evaluates w = loc + (scale * kWhInvSd) * sum with the constant folded into the edge record
+      w[b] = fmaf(v[b], p.p1[pi] * kWhInvSd, p.p0[pi]);
+      if (p.relu) w[b] = fmaxf(w[b], 0.f);
+    }
+    const int64_t o = ((int64_t)s * p.E + e) * p.K + ch;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      w_out[o + b] = w[b];
+      if (eps_out) eps_out[o + b] = z[b];
+    }
+  }
+}
+
+}  // namespace stag
+#include "spmm_tc.cuh"
+namespace stag {
+
 // Philox blocks needed by `width` channels: 8 per whole 64-channel group, one per started quad of
 // the first half of the last group
 static int blocks_for(int width) {
@@ -1425,7 +1468,7 @@ static int lpr_log2_for(int nblk) {
 }
 
 struct WsLayout {
-  size_t part_acc, part_w, dp_partial, rec, total;
+  size_t part_acc, part_w, dp_partial, rec, ebnd, total;
 };
 
 static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
@@ -1440,6 +1483,8 @@ static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
   off += align_up((size_t)grid_max * 2 * D8 * 4 + 16, 256);
   L.rec = off;
   off += align_up((size_t)g->num_edges * 16 + 16, 256);
+  L.ebnd = off;
+  off += align_up((size_t)(g->num_edges / TC_UNIT_EDGES + 2) * 4, 256);
   L.total = off;
   return L;
 }
@@ -1450,7 +1495,7 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 static int check_noise(const StagNoise* n, int D, int64_t E, const char* who) {
   STAG_CHECK_ARG(n != nullptr, "%s: null noise spec", who);
-  STAG_CHECK_ARG(n->kind >= STAG_NOISE_NONE && n->kind <= STAG_NOISE_BERNOULLI, "%s: bad noise kind %d", who, n->kind);
+  STAG_CHECK_ARG(n->kind >= STAG_NOISE_NONE && n->kind <= STAG_NOISE_NORMAL_HADAMARD, "%s: bad noise kind %d", who, n->kind);
   if (n->kind == STAG_NOISE_NONE) return STAG_OK;
   STAG_CHECK_ARG(n->K == 1 || n->K == D, "%s: noise width K=%d must be 1 or D=%d", who, n->K, D);
   if (n->kind == STAG_NOISE_EXTERNAL) {
@@ -1463,6 +1508,8 @@ static int check_noise(const StagNoise* n, int D, int64_t E, const char* who) {
   STAG_CHECK_ARG(n->p0 != nullptr || (per_edge && E == 0), "%s: null parameter p0", who);
   STAG_CHECK_ARG(n->kind == STAG_NOISE_BERNOULLI || n->p1 != nullptr || (per_edge && E == 0),
                  "%s: null parameter p1", who);
+  if (n->kind == STAG_NOISE_NORMAL_HADAMARD)
+    STAG_CHECK_ARG(n->K % 128 == 0, "%s: the Hadamard generator needs K %% 128 == 0 (K=%d)", who, n->K);
   return STAG_OK;
 }
 
@@ -1730,6 +1777,24 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
   if (noise->kind >= STAG_NOISE_NORMAL && noise->param_shape != STAG_PARAM_SCALAR && noise->K != 1)
     vec = vec && aligned16(noise->p0) && (noise->p1 == nullptr || aligned16(noise->p1));
   if (norm_scale_out && noise->K != 1) vec = vec && aligned16(norm_scale_out);
+  if (noise->kind == STAG_NOISE_NORMAL_HADAMARD) {
+    // tensor-core noise path (spmm_tc.cuh): hubs need no partial sums, a thread owns a channel of the whole row
+    if (g->num_edges == 0) {
+      p.kind = STAG_NOISE_NONE;  // nothing to draw: the streaming kernel's tail clears the rows
+    } else {
+      const bool ok = noise->K == D && D % 128 == 0 && vec && !noise->relu && !noise->in_norm &&
+                      (noise->param_shape == STAG_PARAM_SCALAR || noise->param_shape == STAG_PARAM_EDGE) &&
+                      g->erow && g->eidf && g->num_cols * ldx * 4 < (1ll << 32);
+      if (!ok) {
+        set_error("stag_spmm_fwd: STAG_NOISE_NORMAL_HADAMARD needs K == D, D %% 128 == 0, 16-byte aligned rows, scalar "
+                  "or per-edge parameters, no relu / in_norm, a graph built with erow / eidf and a gathered operand "
+                  "below 4 GB (K=%d D=%d)", noise->K, D);
+        return STAG_EUNSUPPORTED;
+      }
+      p.ebnd = (const int32_t*)((char*)ws + L.ebnd);
+      return launch_tc(p, stream);
+    }
+  }
   rc = launch_agg<false>(p, vec, agg_grid(p), 0, stream);
   if (rc) return rc;
   if (g->num_hubs > 0) {
@@ -1754,6 +1819,10 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   STAG_CHECK_ARG(ldx >= D && ldg >= D && (dx == nullptr || lddx >= D), "stag_spmm_bwd: row strides smaller than D");
   rc = check_noise(noise, D, g->num_edges, "stag_spmm_bwd");
   if (rc) return rc;
+  if (noise->kind == STAG_NOISE_NORMAL_HADAMARD) {
+    set_error("stag_spmm_bwd: STAG_NOISE_NORMAL_HADAMARD has no parameter-gradient path (dX: stag_spmm_fwd on the CSR)");
+    return STAG_EUNSUPPORTED;
+  }
   if (noise->in_norm) {
     set_error("stag_spmm_bwd: in_norm has no fused parameter-gradient path (use the emitted-noise path)");
     return STAG_EUNSUPPORTED;
@@ -1856,7 +1925,7 @@ extern "C" int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_
                                void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   STAG_CHECK_ARG(noise != nullptr && w_out != nullptr, "stag_noise_emit: null argument");
-  STAG_CHECK_ARG(noise->kind >= STAG_NOISE_NORMAL && noise->kind <= STAG_NOISE_BERNOULLI,
+  STAG_CHECK_ARG(noise->kind >= STAG_NOISE_NORMAL && noise->kind <= STAG_NOISE_NORMAL_HADAMARD,
                  "stag_noise_emit: kind %d is not a generated distribution", noise->kind);
   STAG_CHECK_ARG(noise->K > 0 && S > 0 && num_edges >= 0 && num_edges < (1ll << 31), "stag_noise_emit: bad sizes");
   int rc = check_noise(noise, noise->K, num_edges, "stag_noise_emit");
@@ -1873,6 +1942,14 @@ extern "C" int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_
   const int64_t total = (int64_t)S * num_edges * p.nblk;
   const int64_t want = (total + 255) / 256;
   const int grid = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  if (noise->kind == STAG_NOISE_NORMAL_HADAMARD) {
+    const int64_t warps = (int64_t)S * num_edges * (noise->K >> 7);
+    const int64_t ctas = (warps + 7) / 8;
+    emit_wh_kernel<<<(unsigned)(ctas < (int64_t)num_sms() * 16 ? ctas : (int64_t)num_sms() * 16), 256, 0, stream>>>(
+        p, w_out, eps_out);
+    STAG_LAUNCH_CHECK();
+    return STAG_OK;
+  }
   switch (noise->kind) {
     case STAG_NOISE_NORMAL: emit_kernel<STAG_NOISE_NORMAL><<<grid, 256, 0, stream>>>(p, w_out, eps_out); break;
     case STAG_NOISE_UNIFORM: emit_kernel<STAG_NOISE_UNIFORM><<<grid, 256, 0, stream>>>(p, w_out, eps_out); break;

@@ -13,12 +13,15 @@ PyTorch is used for device memory, streams and autograd plumbing only; all compu
 happens in libstag_b200.so.  There is no CPU fallback.
 """
 import ctypes
+import os
 
 import torch
 
 from . import _lib, random as _random
 from .graph import as_graph
 
+# 'auto' = the tensor-core generator wherever the fused kernel takes it, else Box-Muller
+_DEFAULT_NORMAL_GENERATOR = "boxmuller"
 _KIND = {"normal": _lib.NOISE_NORMAL, "uniform": _lib.NOISE_UNIFORM, "bernoulli": _lib.NOISE_BERNOULLI}
 
 
@@ -48,13 +51,22 @@ class NoiseSpec:
     relu, in_norm    stag/layers.py:98-105
     seed, offset     Philox key / call counter (reserved at construction)
     sample_base      global index of the first Monte-Carlo sample of this call
+    generator        how standard normals are drawn: 'boxmuller' (16-bit Box-Muller in the CUDA cores),
+                     'hadamard' (Walsh-Hadamard mix of random FP8 bytes on the tensor cores,
+                     csrc/spmm_tc.cuh) or None = hadamard wherever the fused kernel takes it (K a
+                     multiple of 128, scalar or per-edge parameters without gradients, no relu / in-norm;
+                     env STAG_NORMAL_GENERATOR overrides).  The forward, the transposed pass and
+                     ``materialize`` of one spec always use the same generator.
     """
 
     def __init__(self, kind, p0, p1, K, num_edges, relu=False, in_norm=False, seed=None, offset=None,
-                 sample_base=0, n_samples=1, batched=False):
+                 sample_base=0, n_samples=1, batched=False, generator=None):
         if kind not in _KIND:
             raise ValueError("unsupported noise kind %r" % (kind,))
+        if generator not in (None, "boxmuller", "hadamard"):
+            raise ValueError("generator must be None, 'boxmuller' or 'hadamard'; got %r" % (generator,))
         self.kind = kind
+        self.generator = generator
         self.K = int(K)
         self.num_edges = int(num_edges)
         self.relu = bool(relu)
@@ -100,6 +112,27 @@ class NoiseSpec:
     @property
     def requires_grad(self):
         return any(p is not None and p.requires_grad for p in (self.p0, self.p1))
+
+    @property
+    def hadamard_ok(self):
+        """The tensor-core generator can serve every pass of this spec."""
+        return (self.kind == "normal" and self.K % 128 == 0 and not self.relu and not self.in_norm
+                and self.param_shape in (_lib.PARAM_SCALAR, _lib.PARAM_EDGE) and not self.requires_grad)
+
+    @property
+    def lib_kind(self):
+        """STAG_NOISE_* of this spec (one generator for forward, backward and materialize)."""
+        if self.kind != "normal":
+            return _KIND[self.kind]
+        gen = self.generator or os.environ.get("STAG_NORMAL_GENERATOR") or _DEFAULT_NORMAL_GENERATOR
+        if gen == "hadamard":
+            if not self.hadamard_ok:
+                raise ValueError("generator='hadamard' needs K % 128 == 0, scalar or per-edge parameters "
+                                 "without gradients and no relu / in-norm")
+            return _lib.NOISE_NORMAL_HADAMARD
+        if gen == "auto" and self.hadamard_ok:
+            return _lib.NOISE_NORMAL_HADAMARD
+        return _lib.NOISE_NORMAL
 
     def with_samples(self, n_samples, sample_base=0):
         out = NoiseSpec.__new__(NoiseSpec)
@@ -152,7 +185,7 @@ class _NoiseEmit(torch.autograd.Function):
         need_raw = spec.kind != "bernoulli" and any(
             p is not None and p.requires_grad for p in (p0, p1))
         raw = torch.empty_like(w) if need_raw else None
-        nz = _fill_noise(spec, _KIND[spec.kind], K, p0c, p1c, None, False, False, spec.sample_base,
+        nz = _fill_noise(spec, spec.lib_kind, K, p0c, p1c, None, False, False, spec.sample_base,
                          spec.seed, spec.offset, spec.param_shape)
         with torch.cuda.device(dev):
             _lib.check(lib.stag_noise_emit(ctypes.byref(nz), E, S, w.data_ptr(), _ptr(raw), _stream(dev)))
@@ -340,7 +373,7 @@ def stochastic_aggregate(graph, feat, edge_weight=None, reduce="sum", src_scale=
             raise ValueError("noise spec was made for %d edges, graph has %d" % (spec.num_edges, E))
         if spec.K not in (1, D):
             raise ValueError("noise width K=%d must be 1 or feat width %d" % (spec.K, D))
-        cfg.update(kind=_KIND[spec.kind], K=spec.K, relu=spec.relu, in_norm=spec.in_norm,
+        cfg.update(kind=spec.lib_kind, K=spec.K, relu=spec.relu, in_norm=spec.in_norm,
                    sample_base=spec.sample_base, seed=spec.seed, offset=spec.offset,
                    param_shape=spec.param_shape)
         p0, p1 = spec.p0, spec.p1
