@@ -51,6 +51,7 @@ struct AggParams {
   const int32_t* eidf;       // edge id of every stored edge, bit 31 set on the last edge of its row
   const int4* rec;           // per-call edge records (edge_record_kernel), workspace
   const int32_t* ebnd;       // tensor-core path: edge boundaries of the units (tc_bounds_kernel), workspace
+  const uint32_t* rowoff;    // tensor-core path: byte offset of the output row of every stored edge, workspace
   int nunits;
   int num_items;
   uint32_t rk[2 * kPhiloxRounds];  // Philox round keys
@@ -1468,7 +1469,7 @@ static int lpr_log2_for(int nblk) {
 }
 
 struct WsLayout {
-  size_t part_acc, part_w, dp_partial, rec, ebnd, total;
+  size_t part_acc, part_w, dp_partial, rec, ebnd, rowoff, total;
 };
 
 static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
@@ -1485,6 +1486,8 @@ static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
   off += align_up((size_t)g->num_edges * 16 + 16, 256);
   L.ebnd = off;
   off += align_up((size_t)(g->num_edges / TC_UNIT_EDGES + 2) * 4, 256);
+  L.rowoff = off;
+  off += align_up((size_t)g->num_edges * 4 + 16, 256);
   L.total = off;
   return L;
 }
@@ -1784,7 +1787,7 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
     } else {
       const bool ok = noise->K == D && D % 128 == 0 && vec && !noise->relu && !noise->in_norm &&
                       (noise->param_shape == STAG_PARAM_SCALAR || noise->param_shape == STAG_PARAM_EDGE) &&
-                      g->erow && g->eidf && g->num_cols * ldx * 4 < (1ll << 32);
+                      g->erow && g->eidf && g->num_cols * ldx * 4 < (1ll << 32) && g->num_rows * ldo * 4 < (1ll << 32);
       if (!ok) {
         set_error("stag_spmm_fwd: STAG_NOISE_NORMAL_HADAMARD needs K == D, D %% 128 == 0, 16-byte aligned rows, scalar "
                   "or per-edge parameters, no relu / in_norm, a graph built with erow / eidf and a gathered operand "
@@ -1792,6 +1795,7 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
         return STAG_EUNSUPPORTED;
       }
       p.ebnd = (const int32_t*)((char*)ws + L.ebnd);
+      p.rowoff = (const uint32_t*)((char*)ws + L.rowoff);
       return launch_tc(p, stream);
     }
   }

@@ -32,12 +32,13 @@
 
 namespace stag {
 
-constexpr int TC_T = 128;        // edges per tile = MMA N
+constexpr int TC_T = 128;        // edges per tile = MMA N (64 with 3 CTAs per SM measured slower: 3.1 vs 3.0 ms)
 constexpr int TC_THREADS = 128;  // one warpgroup: warp w owns TMEM lanes (= channels) 32w .. 32w+31
 constexpr int TC_CE = 8;         // edges per gather chunk
 constexpr int TC_NCH = TC_T / TC_CE;
 constexpr int TC_RING = 8;       // gather ring slots (chunks) per warp; the chunk loop is unrolled by it
 constexpr int TC_LOOK = 6;       // chunks in flight
+constexpr int TC_CTAS = 2;       // CTAs per SM (shared memory; TMEM: 2 * TC_T columns each)
 constexpr int TC_UNIT_EDGES = 2048;
 constexpr uint32_t TC_H_BYTES = 128 * 128, TC_B_BYTES = TC_T * 128;
 constexpr uint32_t TC_XRING = TC_RING * TC_CE * 128;  // per warp: 128 bytes (32 channels) per edge
@@ -65,7 +66,7 @@ __global__ void tc_bounds_kernel(const int32_t* __restrict__ indptr, int N, int6
 
 // per-call edge records: both degree scalings, the distribution parameters and the variance constant of the
 // Hadamard mix folded into (A, B): w * scale = A + B * (raw sum);  .x = byte offset of the gathered row
-__global__ void tc_record_kernel(const AggParams p, int4* __restrict__ rec) {
+__global__ void tc_record_kernel(const AggParams p, int4* __restrict__ rec, uint32_t* __restrict__ rowoff) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p.E) return;
   const int idx = __ldg(p.indices + j);
@@ -77,6 +78,7 @@ __global__ void tc_record_kernel(const AggParams p, int4* __restrict__ rec) {
   const float a = sc * __ldg(p.p0 + pi);
   const float b = sc * __ldg(p.p1 + pi) * kWhInvSd;
   rec[j] = make_int4((int)((uint32_t)idx * (uint32_t)p.ldx * 4u), ef, __float_as_int(a), __float_as_int(b));
+  rowoff[j] = (uint32_t)row * (uint32_t)p.ldo * 4u;  // byte offset of the output row
 }
 
 struct TcTile {
@@ -147,7 +149,7 @@ __device__ __forceinline__ void tc_ldtm8_wait(uint32_t (&v)[8]) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) agg_tc_kernel(const AggParams p) {
+__global__ void __launch_bounds__(TC_THREADS, TC_CTAS) agg_tc_kernel(const AggParams p) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   __shared__ uint64_t mma_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -199,7 +201,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) agg_tc_kernel(const AggParams p
   // kind::f8f6f4, A = B = E4M3 (format 0), fp32 accumulate, both K-major, N = 128, M = 128
   const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_T >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint64_t h_desc = tc_desc(h_s);
-  const uint32_t ldo4 = (uint32_t)p.ldo * 4u;
 
   // ---- tile cursor (uniform across the CTA) ------------------------------------------------------------
   const int G = p.D >> 7;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) agg_tc_kernel(const AggParams p
       const char* r = reinterpret_cast<const char*>(p.rec + (off ? 0 : t.e0 + i));
       cp_async8(meta_s + (uint32_t)(slot * TC_T + i) * 8u, r, off);
       cp_async8(ab_s + (uint32_t)(slot * TC_T + i) * 8u, r + 8, off);
-      cp_async4(row_s + (uint32_t)(slot * TC_T + i) * 4u, p.erow + (off ? 0 : t.e0 + i), off);
+      cp_async4(row_s + (uint32_t)(slot * TC_T + i) * 4u, p.rowoff + (off ? 0 : t.e0 + i), off);
     }
   };
   // random bytes of a tile: row n of the B operand = the 128 bytes of edge n (8 Philox blocks); this thread makes
@@ -321,6 +322,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) agg_tc_kernel(const AggParams p
 
 #pragma unroll 1
     for (int h = 0; h < TC_NCH / TC_RING; ++h) {
+      // the tile the chunks requested from the second half on belong to
+      const bool last_h = h == TC_NCH / TC_RING - 1;
+      const int la_n = last_h ? d1.n : d0.n;
+      const char* la_xb = last_h ? d1.xb : d0.xb;
+      const uint32_t la_meta = last_h ? meta1 : meta0;
 #pragma unroll
       for (int c = 0; c < TC_RING; ++c) {
         const int jb = (h * TC_RING + c) * TC_CE;  // first edge of the chunk
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) agg_tc_kernel(const AggParams p
           float4 ab[TC_CE / 2];
 #pragma unroll
           for (int e = 0; e < TC_CE / 2; ++e) ab[e] = lds128f(ab0 + (uint32_t)(jb + 2 * e) * 8u);
-          const uint32_t fm = ((c < 4 ? (h ? fmask[2] : fmask[0]) : (h ? fmask[3] : fmask[1])) >> ((c & 3) * 8)) & 0xFFu;
+          const uint32_t fm = ((h ? fmask[2 + (c >> 2)] : fmask[c >> 2]) >> ((c & 3) * 8)) & 0xFFu;
           tc_ldtm8_wait(z);
           float w[TC_CE];
 #pragma unroll
@@ -352,17 +358,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) agg_tc_kernel(const AggParams p
             for (int e = 0; e < TC_CE; ++e) {
               acc = fmaf(w[e], xv[e], acc);
               if (fm & (1u << e)) {  // last edge of a row: write it, start the next one
-                const uint32_t rw = (uint32_t)lds32(row0 + (uint32_t)(jb + e) * 4u);
-                __stcs(reinterpret_cast<float*>(d0.ob + rw * ldo4), acc);
+                const uint32_t ro = (uint32_t)lds32(row0 + (uint32_t)(jb + e) * 4u);
+                __stcs(reinterpret_cast<float*>(d0.ob + ro), acc);
                 acc = 0.f;
               }
             }
           }
         }
         // request the chunk TC_LOOK ahead into the slot consumed TC_RING - TC_LOOK chunks ago
-        const bool nxt = h * TC_RING + c + TC_LOOK >= TC_NCH;  // ... which belongs to the next tile
-        gather(nxt ? d1.n : d0.n, nxt ? d1.xb : d0.xb, nxt ? meta1 : meta0,
-               ((h * TC_RING + c + TC_LOOK) % TC_NCH) * TC_CE, (c + TC_LOOK) % TC_RING);
+        if (c + TC_LOOK < TC_RING)  // same half
+          gather(d0.n, d0.xb, meta0, (h * TC_RING + c + TC_LOOK) * TC_CE, c + TC_LOOK);
+        else  // next half: of this tile, or the first half of the next tile
+          gather(la_n, la_xb, la_meta, ((last_h ? 0 : (h + 1) * TC_RING) + c + TC_LOOK - TC_RING) * TC_CE,
+                 (c + TC_LOOK) % TC_RING);
         cp_async_commit();
       }
     }
@@ -382,14 +390,15 @@ static int launch_tc(const AggParams& p_, cudaStream_t stream) {
   AggParams p = p_;
   p.nunits = (int)((p.E + TC_UNIT_EDGES - 1) / TC_UNIT_EDGES);
   if (p.E > 0) {
-    tc_record_kernel<<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(p, const_cast<int4*>(p.rec));
+    tc_record_kernel<<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(p, const_cast<int4*>(p.rec),
+                                                                        const_cast<uint32_t*>(p.rowoff));
     STAG_LAUNCH_CHECK();
     tc_bounds_kernel<<<(unsigned)((p.nunits + 256) / 256), 256, 0, stream>>>(p.indptr, p.N, p.E, p.nunits,
                                                                             const_cast<int32_t*>(p.ebnd));
     STAG_LAUNCH_CHECK();
   }
   const int64_t total = (int64_t)p.nunits * p.S * (p.D >> 7);
-  const int64_t cap = (int64_t)num_sms() * 2;
+  const int64_t cap = (int64_t)num_sms() * TC_CTAS;
   const int grid = (int)(total < 1 ? 1 : (total < cap ? total : cap));
   STAG_CUDA(cudaFuncSetAttribute(agg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   agg_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(p);

@@ -119,3 +119,25 @@ def test_golden_reproducible_from_live_reference(tmp_path, monkeypatch):
         assert sorted(a.files) == sorted(b.files)
         for k in a.files:
             np.testing.assert_allclose(a[k], b[k], rtol=1e-5, atol=1e-6)
+
+
+def test_hadamard_generator_restatement_law():
+    """The numpy restatement of the tensor-core generator (oracle/ref_philox.py): constants, orthogonality of the
+    mixing matrix, exactness of the sums and the law of the output on 1.3e6 draws."""
+    from scipy import stats
+    from oracle import ref_philox as rp
+    H = rp.hadamard_matrix()
+    assert np.array_equal(H @ H.T, 128 * np.eye(128))
+    v = rp.e4m3_value((np.arange(256) & rp.WH_AND) | rp.WH_OR)
+    m2, m4 = (v ** 2).mean(), (v ** 4).mean()
+    assert m2 == 105186885 / 524288
+    assert abs(m4 / m2 ** 2 - 3.0) < 1e-3                      # input law: excess kurtosis 8e-4
+    assert abs(float(rp.WH_INV_SD) - 1 / np.sqrt(128 * m2)) < 1e-9
+    assert np.abs(v).max() * 128 < 2 ** 12 and np.all(v * 256 == np.round(v * 256))   # sums exact in fp32
+    s = rp.hadamard_sums(5000, 256, 1, 42, 3)
+    assert np.array_equal(s.astype(np.float32).astype(np.float64), s)
+    z = rp.hadamard_normal(5000, 256, 1, 42, 3).astype(np.float64)
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2.0 / n)
+    assert abs(stats.kurtosis(z.ravel())) < 5 * np.sqrt(24.0 / n)
+    assert stats.kstest(z.ravel(), "norm").pvalue > 1e-3
