@@ -154,3 +154,25 @@ def test_early_stopping_contract():
     assert es([0.5, 0.5], m) is False and es.best_state is not None
     assert es([0.6, 0.6], m) is False
     assert es([0.7, 0.7], m) is True
+
+
+@pytest.mark.parametrize("out_features,hidden", [(1, None), (16, None), (16, 8)])
+def test_amortized_condition_equals_the_concatenated_form(out_features, hidden):
+    """AmortizedDistribution.condition applies the first Linear to the node rows (split into its source / destination
+    halves) instead of the [E, 2 D] concat of the reference (stag/distributions.py:221-233): same parameters."""
+    import torch
+    import stag_b200 as stag
+    torch.manual_seed(0)
+    N, E, D = 30, 200, 16
+    g = stag.Graph(torch.randint(0, N, (E,)), torch.randint(0, N, (E,)), N)
+    q = stag.distributions.AmortizedDistribution(D, out_features, hidden_features=hidden).double()
+    for feat in (torch.randn(N, D, dtype=torch.float64), torch.randn(3, N, D, dtype=torch.float64)):
+        q.condition(g, feat)
+        src, dst = g.edges()
+        h = q.embedding_mlp(torch.cat([feat.index_select(-2, src), feat.index_select(-2, dst)], dim=-1))
+        for key in q.new_parameter_names:
+            ref = q.parameters_mlp[key](h)
+            assert q.new_parameters[key].shape == ref.shape
+            assert torch.allclose(q.new_parameters[key], ref, rtol=1e-12, atol=1e-12)
+        dist = q.base_distribution
+        assert dist.loc.shape[-2:] == (E, out_features) and (dist.scale > 0).all()
