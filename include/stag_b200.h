@@ -199,6 +199,17 @@ STAG_API int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_t 
 STAG_API int stag_segment_reduce(const float* feat, int64_t ldf, const int32_t* node_ptr, int32_t num_graphs,
                         int32_t D, int mean, float* out, int64_t ldo, void* stream);
 
+/* Likelihood epilogue (stag/models.py:69-72, stag/likelihoods.py:13-38): for each of the S Monte-Carlo outputs
+ *   nll_out[s] = mean over the masked nodes of -log_prob(probs[s], y)
+ * kind 0: Categorical(probs=.) -- probs renormalised, clamped to [eps, 1-eps], log, gathered at y (int64 [N]);
+ * kind 1: Bernoulli(probs=.)   -- y float [N,C] (row stride ldy), mean over the masked rows x C labels;
+ * exactly as torch.distributions evaluates them.  mask: uint8 [N] or NULL.  count_out[0] = number of terms of each
+ * mean.  dprobs (optional, same strides as probs) receives d(count * nll_out[s]) / d probs[s] in the same pass. */
+STAG_API size_t stag_nll_workspace_bytes(int64_t N, int32_t S);
+STAG_API int stag_nll(const float* probs, int64_t ld, int64_t sample_stride, int64_t N, int32_t C, int32_t S,
+             int kind, const void* y, int64_t ldy, const uint8_t* mask, float* nll_out, float* count_out,
+             float* dprobs, void* ws, size_t ws_bytes, void* stream);
+
 /* Dense feature transform agg @ W (stag/zoo/gcn.py:97-98) on tcgen05 tensor cores with TMEM
  * accumulators; fp32 in / fp32 out computed as 3xTF32 (fp32-level accuracy), fused epilogue
  *   out[m,n] = act( row_scale[m] * sum_k a[m,k]*w[k,n] + bias[n] ),  act: 0 none, 1 relu.

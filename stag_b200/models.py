@@ -97,12 +97,16 @@ class StagModel(torch.nn.Module):
         if kl_scaling is None:
             kl_scaling = self.kl_scaling
         outs = self._forward_samples(graph, feat, n_samples)
-        total_nll = 0.0
-        for s in range(n_samples):
-            nll = -self.likelihood.log_prob(outs[s], y)
-            if mask is not None:
-                nll = nll[mask]
-            total_nll = total_nll + nll.mean()
+        if hasattr(self.likelihood, "nll_samples"):
+            # all samples in one fused pass on CUDA (stag_nll), torch.distributions otherwise
+            total_nll = self.likelihood.nll_samples(outs, y, mask).sum()
+        else:
+            total_nll = 0.0
+            for s in range(n_samples):
+                nll = -self.likelihood.log_prob(outs[s], y)
+                if mask is not None:
+                    nll = nll[mask]
+                total_nll = total_nll + nll.mean()
         reg = 0.0
         for layer in self.layers:
             if layer.vi:

@@ -427,6 +427,50 @@ class _SegmentReduce(torch.autograd.Function):
         return torch.repeat_interleave(go, bnn, dim=0).reshape(ctx.shape), None, None
 
 
+class _FusedNLL(torch.autograd.Function):
+    """stag_nll: masked mean negative log-likelihood of S sample outputs [S,N,C] -> [S], gradient emitted by the
+    same kernel pass (stag/models.py:69-72 over torch.distributions' Categorical / Bernoulli)."""
+
+    @staticmethod
+    def forward(ctx, probs, y, mask, kind):
+        _require_cuda(probs, "likelihood input")
+        lib = _lib.load()
+        dev = probs.device
+        S, N, C = probs.shape
+        pr = probs.detach().to(torch.float32).contiguous()
+        yy = y.to(torch.int64).contiguous() if kind == 0 else y.to(torch.float32).contiguous()
+        mk = None if mask is None else mask.to(torch.uint8).contiguous()
+        nll = torch.empty(S, dtype=torch.float32, device=dev)
+        count = torch.empty(1, dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[0]
+        dpr = torch.empty_like(pr) if need else None
+        with torch.cuda.device(dev):
+            wsb = lib.stag_nll_workspace_bytes(N, S)
+            ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+            _lib.check(lib.stag_nll(pr.data_ptr(), C, N * C, N, C, S, kind, yy.data_ptr(), C if kind == 1 else 0,
+                                    _ptr(mk), nll.data_ptr(), count.data_ptr(), _ptr(dpr), ws.data_ptr(),
+                                    ws.numel(), _stream(dev)))
+        ctx.save_for_backward(dpr, count)
+        return nll
+
+    @staticmethod
+    def backward(ctx, g):
+        dpr, count = ctx.saved_tensors
+        if dpr is None:
+            return None, None, None, None
+        return dpr * (g.to(torch.float32) / count).reshape(-1, 1, 1), None, None, None
+
+
+def fused_nll(probs, y, mask=None, kind="categorical"):
+    """``[S]`` masked mean NLLs of ``probs [S,N,C]`` (or ``[N,C]`` -> scalar) under Categorical(probs=.) with labels
+    ``y [N]`` or Bernoulli(probs=.) with labels ``y [N,C]``: one kernel pass for all samples, forward and gradient."""
+    squeeze = probs.dim() == 2
+    if squeeze:
+        probs = probs.unsqueeze(0)
+    out = _FusedNLL.apply(probs, y, mask, {"categorical": 0, "bernoulli": 1}[kind])
+    return out[0] if squeeze else out
+
+
 class _DenseTransform(torch.autograd.Function):
     """out = act(row_scale * (a @ weight) + bias) on stag_gemm_tcgen05 (3xTF32, fp32 accuracy).
     Backward: dA = g @ W^T through the same kernel, dW / dbias by torch reductions."""
