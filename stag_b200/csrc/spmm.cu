@@ -209,6 +209,7 @@ template <int KIND>
 __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, int scales_only) {
   // scales_only: 0 = (A, B) as documented above, 1 = the two scalings only (gradient / two-sum kernels),
   // 2 = like 0 with sqrt(2 ln 2) folded into B of Normal noise (agg_stream3_kernel takes sqrt(-lg2 u1) as radius)
+  // 3 = like 0 with the variance constant of the Hadamard mix folded into B (agg_wh_stream_kernel)
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= p.E) return;
   const int idx = __ldg(p.indices + j);
@@ -224,7 +225,7 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, in
   const float pa = __ldg(p.p0 + pi);
   const float pb = KIND != STAG_NOISE_BERNOULLI ? __ldg(p.p1 + pi) : 0.f;
   float a, b;
-  if (KIND == STAG_NOISE_NORMAL) { a = sc * pa; b = sc * pb * (scales_only == 2 ? 1.1774100225154747f : 1.0f); }
+  if (KIND == STAG_NOISE_NORMAL) { a = sc * pa; b = sc * pb * (scales_only == 2 ? 1.1774100225154747f : (scales_only == 3 ? kWhInvSd : 1.0f)); }
   else if (KIND == STAG_NOISE_UNIFORM) { a = sc * pa; b = sc * (pb - pa); }
   else { a = pa; b = sc; }
   if (scales_only == 2 && KIND == STAG_NOISE_UNIFORM) {
@@ -1796,7 +1797,18 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
       }
       p.ebnd = (const int32_t*)((char*)ws + L.ebnd);
       p.rowoff = (const uint32_t*)((char*)ws + L.rowoff);
-      return launch_tc(p, stream);
+      // two forms of the kernel (spmm_tc.cuh): 2 = tensor cores feeding the 16-channels-per-lane stream (default, needs
+      // the stream items), 1 = channel per thread
+      static const char* form = getenv("STAG_TC_FORM");
+      if ((form && atoi(form) == 1) || !g->items) return launch_tc(p, stream);
+      rc = launch_wh_stream(p, stream);
+      if (rc) return rc;
+      if (g->num_hubs > 0) {
+        const int64_t total = (int64_t)S * g->num_hubs * D;
+        hub_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, 0);
+        STAG_LAUNCH_CHECK();
+      }
+      return STAG_OK;
     }
   }
   rc = launch_agg<false>(p, vec, agg_grid(p), 0, stream);

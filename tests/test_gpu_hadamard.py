@@ -77,6 +77,19 @@ def test_moments_ks_independence():
     assert np.abs(C2 - np.eye(K)).max() < 6 / np.sqrt(E)
 
 
+def test_channel_per_thread_form_in_a_fresh_process():
+    """agg_tc_kernel (STAG_TC_FORM=1) against the same oracle: the fused parity cases of this file, rerun."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("STAG_TC_FORM") == "1":
+        pytest.skip("already running the channel-per-thread form")
+    env = dict(os.environ, STAG_TC_FORM="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-k",
+                        "fused_forward or bitwise or per_edge"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("N,E,D,S,shared,hub", [
     (500, 3000, 128, 3, True, 0), (500, 3000, 128, 3, False, 0), (3000, 40000, 256, 2, False, 9000),
     (300, 100, 128, 1, True, 0), (700, 9000, 384, 2, True, 2500), (5000, 70001, 128, 5, False, 300)])
