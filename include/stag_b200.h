@@ -175,7 +175,8 @@ STAG_API int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, int6
  *   NORMAL : dparam0 = sum dw (d loc), dparam1 = sum dw*eps (d scale)
  *   UNIFORM: dparam0 = sum dw*(1-u) (d low), dparam1 = sum dw*u (d high)
  * reduced to the parameter shape: SCALAR -> [1], CHANNEL -> [K], EDGE -> [E], EDGE_CHANNEL -> [E,K]
- * (EDGE shapes require S == 1 and ACCUMULATE into dparam*, i.e. the caller zeroes them once).
+ * (EDGE shapes ACCUMULATE into dparam*, summed over the S samples, i.e. the caller zeroes them once; any S when the
+ * graph carries erow -- an edge-parallel kernel -- else S == 1).
  * SCALAR / CHANNEL results OVERWRITE dparam* and are summed over the S samples.
  * dx may be NULL (first layer: features need no gradient).  Not valid with in_norm.
  */

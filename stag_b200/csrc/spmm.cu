@@ -1367,6 +1367,95 @@ __global__ void param_finalize_kernel(const float* __restrict__ partial, int nct
   }
 }
 
+// Per-edge parameter gradients (EDGE / EDGE_CHANNEL shapes: the [E,1] / [E,K] outputs of AmortizedDistribution,
+// stag/distributions.py:221-242) for any number of samples in one launch.  Edge-parallel: half a warp owns one stored
+// edge, a lane one Philox block (8 channels) of it at a time; it reads the source row x[u] and the upstream row
+// dout[v], regenerates the raw variates of (edge, sample) and reduces
+//     dw[s,e,c] = (src_scale[u] x[s,u,c]) (dst_scale[v] dout[s,v,c])          (the SDDMM term, never stored)
+//     NORMAL : d p0 += dw, d p1 += dw eps        UNIFORM: d p0 += dw (1 - u), d p1 += dw u        (relu: dw masked)
+// over the samples (and, for the EDGE shape, over the channels: 4 shuffle steps).  One writer per edge, fixed
+// summation order: deterministic.  Results ACCUMULATE into dp0 / dp1 (the caller zeroes them once).
+// p holds the transposed roles of stag_spmm_bwd: p.x = dout (gscale = dst_scale), p.xrow = x (rscale = src_scale).
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(256) edge_param_grads_kernel(const AggParams p) {
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  const int64_t nhw = (int64_t)gridDim.x * (blockDim.x >> 4);
+  const int64_t hw0 = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  const int64_t trips = (p.E + nhw - 1) / nhw;  // both halves of a warp make the same number of trips (shuffles below)
+  const int nblk = p.nblk;
+  for (int64_t it = 0; it < trips; ++it) {
+    const int64_t j = hw0 + it * nhw;
+    const bool on = j < p.E;
+    const int u = on ? __ldg(p.erow + j) : 0;
+    const int v = on ? __ldg(p.indices + j) : 0;
+    const int e = on ? __ldg(p.eid + j) : 0;
+    float sc = p.gscale ? __ldg(p.gscale + v) : 1.0f;
+    if (p.rscale) sc *= __ldg(p.rscale + u);
+    const bool per_channel = p.pshape == STAG_PARAM_EDGE_CHANNEL;
+    const float P0 = (on && !per_channel) ? __ldg(p.p0 + e) : 0.f;
+    const float P1 = (on && !per_channel) ? __ldg(p.p1 + e) : 0.f;
+    float t0 = 0.f, t1 = 0.f;
+    if (on) {
+      for (int b = hl; b < nblk; b += 16) {
+        const int c = first_chan(0, b);
+        float d0[8], d1[8], pa[8], pb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          d0[i] = d1[i] = 0.f;
+          const int ch = chan(c, i);
+          pa[i] = per_channel ? (ch < p.D ? __ldg(p.p0 + (int64_t)e * p.K + ch) : 0.f) : P0;
+          pb[i] = per_channel ? (ch < p.D ? __ldg(p.p1 + (int64_t)e * p.K + ch) : 0.f) : P1;
+        }
+        for (int s = 0; s < p.S; ++s) {
+          float xr[8], gv[8], raw[8];
+          load8<VEC>(p.xrow + (int64_t)s * p.xr_ss + (int64_t)u * p.ldxr, c, p.D, xr);
+          load8<VEC>(p.x + (int64_t)s * p.x_ss + (int64_t)v * p.ldx, c, p.D, gv);
+          const uint32_t smp = (uint32_t)(p.sample_base + s);
+          if (p.K == 1) {
+            const float r1 = raw_first(KIND, (uint32_t)e, smp, p.key);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) raw[i] = r1;
+          } else {
+            raw_oct<KIND>((uint32_t)e, (uint32_t)b, smp, p.key, raw);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float dw = xr[i] * gv[i] * sc;  // zero beyond D (load8 pads)
+            if (p.relu && !(transform<KIND>(raw[i], pa[i], pb[i]) > 0.f)) dw = 0.f;
+            const float e1 = dw * raw[i];
+            d1[i] += e1;
+            d0[i] += KIND == STAG_NOISE_NORMAL ? dw : dw - e1;
+          }
+        }
+        if (per_channel) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int ch = chan(c, i);
+            if (ch < p.D) {
+              p.dp0[(int64_t)e * p.K + ch] += d0[i];
+              p.dp1[(int64_t)e * p.K + ch] += d1[i];
+            }
+          }
+        } else {
+          t0 += sum8(d0);
+          t1 += sum8(d1);
+        }
+      }
+    }
+    if (!per_channel) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      }
+      if (on && hl == 0) {
+        p.dp0[e] += t0;
+        p.dp1[e] += t1;
+      }
+    }
+  }
+}
+
 // noise materialisation (compat path + RNG tests): w[s,e,c]
 template <int KIND>
 __global__ void emit_kernel(const AggParams p, float* __restrict__ w_out, float* __restrict__ eps_out) {
@@ -1849,7 +1938,11 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   fill_graph(p, g);
   fill_noise(p, noise, D);
   const bool edge_params = param_grads && p.pshape >= STAG_PARAM_EDGE;
-  STAG_CHECK_ARG(!edge_params || S == 1, "stag_spmm_bwd: per-edge parameter gradients require S == 1 (got %d)", S);
+  // per-edge parameter gradients for any S need the row of every stored edge (edge-parallel kernel); without it the
+  // row-per-group family takes one sample per launch
+  const bool edge_parallel = edge_params && g->erow != nullptr;
+  STAG_CHECK_ARG(!edge_params || edge_parallel || S == 1,
+                 "stag_spmm_bwd: per-edge parameter gradients on a graph without erow require S == 1 (got %d)", S);
   if (g->num_rows == 0) {
     if (param_grads && !edge_params) {
       const size_t n = p.pshape == STAG_PARAM_SCALAR ? 1 : (size_t)D;
@@ -1880,6 +1973,35 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
     vec = vec && aligned16(noise->external) && (dw_external == nullptr || aligned16(dw_external));
   if (param_grads && noise->param_shape != STAG_PARAM_SCALAR && noise->K != 1)
     vec = vec && aligned16(noise->p0) && aligned16(noise->p1) && aligned16(dparam0) && aligned16(dparam1);
+  if (edge_parallel) {
+    // dX: the transposed aggregation on the forward kernels (streaming kernel for per-edge parameters without relu)
+    if (dx) {
+      AggParams q = p;
+      set_shape(q, D, S, g->num_cols, false, false);
+      q.rec = (const int4*)((char*)ws + L.rec);
+      q.xrow = nullptr; q.dp0 = q.dp1 = nullptr; q.dw_ext = nullptr;
+      rc = launch_agg<false>(q, vec, agg_grid(q), 0, stream);
+      if (rc) return rc;
+      if (g->num_hubs > 0) {
+        const int64_t total = (int64_t)S * g->num_hubs * D;
+        hub_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(q, 0);
+        STAG_LAUNCH_CHECK();
+      }
+    }
+    if (p.E > 0) {
+      const int64_t want = (p.E + 15) / 16;
+      const int egrid = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+      if (noise->kind == STAG_NOISE_NORMAL) {
+        if (vec) edge_param_grads_kernel<STAG_NOISE_NORMAL, true><<<egrid, 256, 0, stream>>>(p);
+        else edge_param_grads_kernel<STAG_NOISE_NORMAL, false><<<egrid, 256, 0, stream>>>(p);
+      } else {
+        if (vec) edge_param_grads_kernel<STAG_NOISE_UNIFORM, true><<<egrid, 256, 0, stream>>>(p);
+        else edge_param_grads_kernel<STAG_NOISE_UNIFORM, false><<<egrid, 256, 0, stream>>>(p);
+      }
+      STAG_LAUNCH_CHECK();
+    }
+    return STAG_OK;
+  }
   const int grid = agg_grid(p);
   const size_t smem = (param_grads && !edge_params) ? (size_t)AGG_WARPS * 2 * p.dpad * sizeof(float) : 0;
   if (smem > 200 * 1024) {

@@ -298,8 +298,9 @@ class _StochasticSpMM(torch.autograd.Function):
                          _lib.PARAM_EDGE_CHANNEL: st.num_edges * K}[pshape]
                     dp0 = torch.zeros(n, dtype=torch.float32, device=dev)
                     dp1 = torch.zeros(n, dtype=torch.float32, device=dev)
-                # per-edge parameter gradients accumulate one sample per launch
-                groups = [(s, 1) for s in range(S)] if edge_params else [(0, S)]
+                # per-edge parameter gradients: all samples in one launch (edge-parallel kernel) when the graph
+                # carries the row of every stored edge, else one sample per launch
+                groups = [(s, 1) for s in range(S)] if (edge_params and not csr.erow) else [(0, S)]
                 for s0, ns_ in groups:
                     nz = noise(cfg["sample_base"] + s0,
                                None if extc is None else extc[s0:s0 + ns_])
