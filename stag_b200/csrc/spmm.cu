@@ -1406,10 +1406,20 @@ __global__ void __launch_bounds__(256) edge_param_grads_kernel(const AggParams p
           pa[i] = per_channel ? (ch < p.D ? __ldg(p.p0 + (int64_t)e * p.K + ch) : 0.f) : P0;
           pb[i] = per_channel ? (ch < p.D ? __ldg(p.p1 + (int64_t)e * p.K + ch) : 0.f) : P1;
         }
+        // the rows of sample s + 1 are requested before sample s is worked on
+        const float* xrp = p.xrow + (int64_t)u * p.ldxr;
+        const float* gvp = p.x + (int64_t)v * p.ldx;
+        float xn[8], gn[8];
+        load8<VEC>(xrp, c, p.D, xn);
+        load8<VEC>(gvp, c, p.D, gn);
         for (int s = 0; s < p.S; ++s) {
           float xr[8], gv[8], raw[8];
-          load8<VEC>(p.xrow + (int64_t)s * p.xr_ss + (int64_t)u * p.ldxr, c, p.D, xr);
-          load8<VEC>(p.x + (int64_t)s * p.x_ss + (int64_t)v * p.ldx, c, p.D, gv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { xr[i] = xn[i]; gv[i] = gn[i]; }
+          if (s + 1 < p.S) {
+            load8<VEC>(xrp + (int64_t)(s + 1) * p.xr_ss, c, p.D, xn);
+            load8<VEC>(gvp + (int64_t)(s + 1) * p.x_ss, c, p.D, gn);
+          }
           const uint32_t smp = (uint32_t)(p.sample_base + s);
           if (p.K == 1) {
             const float r1 = raw_first(KIND, (uint32_t)e, smp, p.key);

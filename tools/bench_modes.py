@@ -27,6 +27,8 @@ onec = torch.ones(D, device=dev); sgc = torch.full((D,), 0.4, device=dev)
 pb = torch.full((1,), 0.8, device=dev)
 lo = torch.full((1,), 0.3, device=dev); hi = torch.full((1,), 1.7, device=dev)
 dp = torch.zeros(2, D, device=dev)
+loc_e = torch.ones(E, 1, device=dev); sg_e = torch.full((E, 1), 0.4, device=dev)
+dpe = torch.zeros(2, E, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
 
 def noise(kind, K, pshape, p0, p1, relu=0, in_norm=0):
@@ -43,6 +45,11 @@ def fwd(nz):
 def bwd(nz):
     _lib.check(lib.stag_spmm_bwd(ctypes.byref(csr), x.data_ptr(), D, N * D, out.data_ptr(), D, N * D, D, S, ctypes.byref(nz),
                                  ss.data_ptr(), ds.data_ptr(), dxb.data_ptr(), D, N * D, dp[0].data_ptr(), dp[1].data_ptr(), 0,
+                                 ws.data_ptr(), ws.numel(), stream))
+
+def bwd_edge(nz):
+    _lib.check(lib.stag_spmm_bwd(ctypes.byref(csr), x.data_ptr(), D, N * D, out.data_ptr(), D, N * D, D, S, ctypes.byref(nz),
+                                 ss.data_ptr(), ds.data_ptr(), dxb.data_ptr(), D, N * D, dpe[0].data_ptr(), dpe[1].data_ptr(), 0,
                                  ws.data_ptr(), ws.numel(), stream))
 
 def t(fn, n=5):
@@ -66,6 +73,9 @@ cases = [
     ("Bernoulli + in-norm (arxiv Bernoulli config)", lambda: fwd(noise(L.NOISE_BERNOULLI, D, L.PARAM_SCALAR, pb, None, in_norm=1)), bench.bytes_fwd(S, False)),
     ("backward dX + d(loc,scale), per-channel params (vi)", lambda: bwd(noise(L.NOISE_NORMAL, D, L.PARAM_CHANNEL, onec, sgc)), bench.bytes_bwd(S, True, False)),
     ("backward dX + d(loc,scale), scalar params (vi)", lambda: bwd(noise(L.NOISE_NORMAL, D, L.PARAM_SCALAR, one, sg)), bench.bytes_bwd(S, True, False)),
+    ("Normal, per-channel noise, per-edge params [E,1] (amortised re)", lambda: fwd(noise(L.NOISE_NORMAL, D, L.PARAM_EDGE, loc_e, sg_e)), bench.bytes_fwd(S, False) + 8 * E),
+    ("backward dX + d(loc,scale)[E,1], 16 samples in one call (amortised re)", lambda: bwd_edge(noise(L.NOISE_NORMAL, D, L.PARAM_EDGE, loc_e, sg_e)), bench.bytes_bwd(S, True, False) + 16 * E),
+    ("Normal via tensor-core Hadamard generator (opt-in)", lambda: fwd(noise(L.NOISE_NORMAL_HADAMARD, D, L.PARAM_SCALAR, one, sg)), bench.bytes_fwd(S, False)),
 ]
 rows = []
 for name, fn, nbytes in cases:
