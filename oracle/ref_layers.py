@@ -18,6 +18,8 @@ def case_kind(name):
         return "sage_" + name.split("_")[1]
     if name.startswith("gin"):
         return "gin"
+    if name.startswith("gat"):
+        return "gat"
     return "gcn"
 
 
@@ -50,6 +52,29 @@ def layer_forward(name, d, feat, w):
         b = t(d["p_bias"]).clone().requires_grad_(True)
         params = {"fc_neigh.weight": Wn, "fc_self.weight": Ws, "bias": b}
         out = R.sage_forward(src, dst, N, feat, w, Ws, Wn, b, aggregator_type=agg)
+    elif kind == "gat":  # stag/zoo/gat.py:89-145: noise [E,H] scales the leaky-relu logits before the softmax
+        Wfc = t(d["p_fc__weight"]).clone().requires_grad_(True)
+        al = t(d["p_attn_l"]).clone().requires_grad_(True)
+        ar = t(d["p_attn_r"]).clone().requires_grad_(True)
+        b = t(d["p_bias"]).clone().requires_grad_(True)
+        Wres = t(d["p_res_fc__weight"]).clone().requires_grad_(True) if "p_res_fc__weight" in d else None
+        params = {"fc.weight": Wfc, "attn_l": al, "attn_r": ar, "bias": b, "res_fc.weight": Wres}
+        H, F = al.shape[1], al.shape[2]
+        ft = (feat @ Wfc.t()).view(N, H, F)
+        el, er = (ft * al).sum(-1), (ft * ar).sum(-1)
+        e = torch.nn.functional.leaky_relu(el[src] + er[dst], 0.2) * w                # [E,H]
+        idx = dst.unsqueeze(-1).expand_as(e)
+        mx = torch.full((N, H), float("-inf"), dtype=e.dtype).scatter_reduce(0, idx, e, reduce="amax", include_self=True)
+        ex = torch.exp(e - mx[dst])
+        a = ex / torch.zeros((N, H), dtype=e.dtype).index_add(0, dst, ex)[dst]         # dgl edge_softmax over in-edges
+        out = torch.zeros((N, H, F), dtype=feat.dtype).index_add(0, dst, ft[src] * a.unsqueeze(-1))
+        if Wres is not None:
+            out = out + (feat @ Wres.t()).view(N, -1, F)
+        out = out + b.view(1, H, F)
+        if name.startswith("gat_last"):
+            out = torch.nn.functional.elu(out.mean(-2))
+        else:
+            out = out.flatten(-2, -1)
     else:  # gin: (1+eps) h_v + sum_e w h_u -> Linear
         Wl = t(d["p_apply_func__weight"]).clone().requires_grad_(True)
         bl = t(d["p_apply_func__bias"]).clone().requires_grad_(True)

@@ -31,6 +31,11 @@ def make_base(name, d):
         m = zoo.GCN(D, out, norm=ref_layers.gcn_norm_of(name), weight=has_w, bias="p_bias" in d)
     elif kind.startswith("sage"):
         m = zoo.GraphSAGE(D, d["p_fc_neigh__weight"].shape[0], aggregator_type=kind.split("_")[1])
+    elif kind == "gat":
+        _, H, F = d["p_attn_l"].shape
+        last = name.startswith("gat_last")
+        m = zoo.GAT(D, F, num_heads=H, last=last, residual="p_res_fc__weight" in d,
+                    activation=torch.nn.functional.elu if last else None)
     else:
         m = zoo.GIN(D, d["p_apply_func__weight"].shape[0])
     sd = {k[2:].replace("__", "."): torch.from_numpy(d[k]) for k in d.files if k.startswith("p_")}
