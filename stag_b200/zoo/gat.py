@@ -73,11 +73,16 @@ class GAT(nn.Module):
         ex = torch.exp(e - mx[dst])
         den = torch.zeros((N, H), dtype=e.dtype, device=e.device).index_add(0, dst, ex)
         a = self.attn_drop(ex / den[dst])                          # [E,H]
-        # weighted aggregation on the fused kernel, one head at a time would waste launches:
-        # expand a to [E,H*F] lazily is E*H*F floats, so aggregate per head with K=1 weights
-        outs = [ops.stochastic_aggregate(g, ft[:, k, :].contiguous(), a[:, k:k + 1].contiguous())
-                for k in range(H)]
-        rst = torch.stack(outs, dim=1)                             # [N,H,F]
+        if a.shape[0] * H * F * 4 <= (256 << 20):
+            # weighted aggregation on the fused kernel in ONE launch over the H*F channels: the attention of head k is the
+            # weight of channels k*F .. (k+1)*F - 1 (external per-channel weights [E, H*F]; autograd sums the SDDMM
+            # gradient back over the F channels of a head)
+            aw = a.unsqueeze(-1).expand(a.shape[0], H, F).reshape(a.shape[0], H * F)
+            rst = ops.stochastic_aggregate(g, ft.reshape(N, H * F), aw).view(N, H, F)
+        else:
+            # large graphs: the expanded weights would be E*H*F floats; one launch per head with [E,1] weights instead
+            outs = [ops.stochastic_aggregate(g, ft[:, k, :].contiguous(), a[:, k:k + 1].contiguous()) for k in range(H)]
+            rst = torch.stack(outs, dim=1)                         # [N,H,F]
         if self.res_fc is not None:
             rst = rst + self.res_fc(h).view(N, -1, F)
         if self.bias is not None:
