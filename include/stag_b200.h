@@ -200,6 +200,13 @@ STAG_API int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_t 
 STAG_API int stag_segment_reduce(const float* feat, int64_t ldf, const int32_t* node_ptr, int32_t num_graphs,
                         int32_t D, int mean, float* out, int64_t ldo, void* stream);
 
+/* Segmented softmax over the in-edges of every destination (dgl.nn.edge_softmax in the reference's GAT,
+ * stag/zoo/gat.py:122): out[e,h] = exp(logits[e,h] - max) / sum over the edges with the same destination.  logits / out
+ * [E,H] in ORIGINAL edge order; csc = the graph built by destination.  Backward: dlogits = a * (da - sum_row a * da). */
+STAG_API int stag_edge_softmax(const StagGraph* csc, const float* logits, int32_t H, float* out, void* stream);
+STAG_API int stag_edge_softmax_bwd(const StagGraph* csc, const float* a, const float* da, int32_t H, float* dlogits,
+                          void* stream);
+
 /* Likelihood epilogue (stag/models.py:69-72, stag/likelihoods.py:13-38): for each of the S Monte-Carlo outputs
  *   nll_out[s] = mean over the masked nodes of -log_prob(probs[s], y)
  * kind 0: Categorical(probs=.) -- probs renormalised, clamped to [eps, 1-eps], log, gathered at y (int64 [N]);

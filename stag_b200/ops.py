@@ -428,6 +428,48 @@ class _SegmentReduce(torch.autograd.Function):
         return torch.repeat_interleave(go, bnn, dim=0).reshape(ctx.shape), None, None
 
 
+class _EdgeSoftmax(torch.autograd.Function):
+    """stag_edge_softmax: softmax of ``logits [E,H]`` over the in-edges of every destination node
+    (dgl.nn.edge_softmax, stag/zoo/gat.py:122), one fused pass per direction."""
+
+    @staticmethod
+    def forward(ctx, logits, g):
+        _require_cuda(logits, "logits")
+        lib = _lib.load()
+        dev = logits.device
+        lg = logits.detach().to(torch.float32).contiguous()
+        E, H = lg.shape
+        out = torch.empty_like(lg)
+        with torch.cuda.device(dev):
+            csc, _ = g._s.csx(True)
+            _lib.check(lib.stag_edge_softmax(ctypes.byref(csc), lg.data_ptr(), H, out.data_ptr(), _stream(dev)))
+        ctx.g = g
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, da):
+        (a,) = ctx.saved_tensors
+        lib = _lib.load()
+        dev = a.device
+        da = da.to(torch.float32).contiguous()
+        dl = torch.empty_like(a)
+        with torch.cuda.device(dev):
+            csc, _ = ctx.g._s.csx(True)
+            _lib.check(lib.stag_edge_softmax_bwd(ctypes.byref(csc), a.data_ptr(), da.data_ptr(), a.shape[1],
+                                                 dl.data_ptr(), _stream(dev)))
+        return dl, None
+
+
+def edge_softmax(graph, logits):
+    """Softmax of ``logits [E,H]`` (or ``[E]``) over the in-edges of each destination node."""
+    g = as_graph(graph)
+    if logits.shape[0] != g._s.num_edges:
+        raise ValueError("logits has %d rows, graph has %d edges" % (logits.shape[0], g._s.num_edges))
+    flat = logits.reshape(logits.shape[0], -1)
+    return _EdgeSoftmax.apply(flat, g).reshape(logits.shape)
+
+
 class _FusedNLL(torch.autograd.Function):
     """stag_nll: masked mean negative log-likelihood of S sample outputs [S,N,C] -> [S], gradient emitted by the
     same kernel pass (stag/models.py:69-72 over torch.distributions' Categorical / Bernoulli)."""

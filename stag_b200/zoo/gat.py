@@ -66,13 +66,8 @@ class GAT(nn.Module):
         e = self.leaky_relu(el[src] + er[dst])                     # [E,H]
         if edge_weight is not None:
             e = edge_weight * e
-        # segmented softmax over the in-edges of each node
-        idx = dst.unsqueeze(-1).expand_as(e)
-        mx = torch.full((N, H), float("-inf"), dtype=e.dtype, device=e.device).scatter_reduce(
-            0, idx, e, reduce="amax", include_self=True)
-        ex = torch.exp(e - mx[dst])
-        den = torch.zeros((N, H), dtype=e.dtype, device=e.device).index_add(0, dst, ex)
-        a = self.attn_drop(ex / den[dst])                          # [E,H]
+        # segmented softmax over the in-edges of each node: one fused pass (stag_edge_softmax)
+        a = self.attn_drop(ops.edge_softmax(g, e))                 # [E,H]
         if a.shape[0] * H * F * 4 <= (256 << 20):
             # weighted aggregation on the fused kernel in ONE launch over the H*F channels: the attention of head k is the
             # weight of channels k*F .. (k+1)*F - 1 (external per-channel weights [E, H*F]; autograd sums the SDDMM

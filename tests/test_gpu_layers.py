@@ -220,3 +220,32 @@ def test_kl_fallback_with_mixture_prior():
     assert rel(out, layer.base_layer(g, x, edge_weight=w)) < 1e-5      # the sample IS the one the kernel used
     (out.sum() + kl).backward()
     assert layer.q_a.loc.grad is not None and torch.isfinite(layer.q_a.log_scale.grad).all()
+
+
+@pytest.mark.parametrize("H", [1, 3, 4, 8, 32])
+def test_edge_softmax_matches_the_scatter_formulation(H):
+    """stag_edge_softmax (forward + backward) == dgl.nn.edge_softmax restated with scatter ops (oracle/dgl_shim),
+    on a graph with a hub destination, duplicate edges and nodes without in-edges."""
+    import stag_b200 as stag
+    g0 = torch.Generator().manual_seed(H)
+    N, E = 300, 4000
+    src, dst = torch.randint(0, N, (E,), generator=g0), torch.randint(5, N, (E,), generator=g0)
+    dst[:900] = 17
+    g = stag.Graph(src, dst, N).to("cuda")
+    logits = (3 * torch.randn(E, H, generator=g0)).cuda()
+    a = logits.clone().requires_grad_(True)
+    b = logits.clone().double().requires_grad_(True)
+    out = stag.ops.edge_softmax(g, a)
+    d = dst.cuda()
+    idx = d.unsqueeze(-1).expand(E, H)
+    mx = torch.full((N, H), float("-inf"), dtype=torch.float64, device="cuda").scatter_reduce(0, idx, b, reduce="amax")
+    ex = torch.exp(b - mx[d])
+    ref = ex / torch.zeros((N, H), dtype=torch.float64, device="cuda").index_add(0, d, ex)[d]
+    assert rel(out, ref) < 1e-6
+    sums = torch.zeros((N, H), device="cuda").index_add(0, d, out)
+    assert torch.allclose(sums[d.unique()], torch.ones_like(sums[d.unique()]), atol=1e-5)
+    gout = torch.randn(E, H, generator=g0).cuda()
+    out.backward(gout)
+    ref.backward(gout.double())
+    assert rel(a.grad, b.grad) < 1e-5
+    assert stag.ops.edge_softmax(g, logits[:, 0]).shape == (E,)
