@@ -42,7 +42,12 @@ void count_launch();  // every kernel launch of the library is counted (stag_lau
 
 constexpr int kHubThreshold = 128;  // rows with more stored edges than this are split
 constexpr int kHubSegment = 128;    // edges per hub segment
-constexpr int kRangeEdges = 64;     // row ranges (stream items) start a new item every this many stored edges
+constexpr int kRangeEdges = 64;     // row ranges (stream items) start a new item every this many stored edges ...
+constexpr int kRangeEdgesSmall = 16;        // ... or every 16 on small graphs, where a launch has few items and the kernels are
+constexpr int64_t kSmallGraphEdges = 65536; // bound by the length of one item's edge walk rather than by throughput
+__host__ __device__ inline int range_edges_for(int64_t num_edges) {
+  return num_edges <= kSmallGraphEdges ? kRangeEdgesSmall : kRangeEdges;
+}
 constexpr int kRangeRows = 256;     // ... and at least every this many rows
 
 int num_sms();  // SM count of the current device (cached per device)

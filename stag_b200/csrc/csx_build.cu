@@ -219,21 +219,21 @@ __global__ void k_reverse_order(const uint32_t* __restrict__ sorted_rows, int64_
 // positions, every kRangeRows rows, and around hub rows (a hub row is an item of its own that the
 // streaming kernel skips: its edges are processed as hub segments).  item = {row0, row1, e0, e1};
 // e1 = -1 marks a hub placeholder.
-__device__ __forceinline__ bool range_starts_at(const int32_t* __restrict__ indptr, int64_t v) {
+__device__ __forceinline__ bool range_starts_at(const int32_t* __restrict__ indptr, int64_t v, int re) {
   if (v == 0 || (v % kRangeRows) == 0) return true;
   const int b = indptr[v], a = indptr[v - 1], c = indptr[v + 1];
-  return (c - b > kHubThreshold) || (b - a > kHubThreshold) || (b / kRangeEdges != a / kRangeEdges);
+  return (c - b > kHubThreshold) || (b - a > kHubThreshold) || (b / re != a / re);
 }
 
-__global__ void k_range_flags(const int32_t* __restrict__ indptr, int64_t N, uint32_t* __restrict__ flags) {
+__global__ void k_range_flags(const int32_t* __restrict__ indptr, int64_t N, int re, uint32_t* __restrict__ flags) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < N) flags[v] = range_starts_at(indptr, v) ? 1u : 0u;
+  if (v < N) flags[v] = range_starts_at(indptr, v, re) ? 1u : 0u;
 }
 
-__global__ void k_range_scatter(const int32_t* __restrict__ indptr, int64_t N, const uint32_t* __restrict__ pos,
+__global__ void k_range_scatter(const int32_t* __restrict__ indptr, int64_t N, int re, const uint32_t* __restrict__ pos,
                                 int32_t* __restrict__ items) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < N && range_starts_at(indptr, v)) {
+  if (v < N && range_starts_at(indptr, v, re)) {
     items[4 * (int64_t)pos[v] + 0] = (int32_t)v;
     items[4 * (int64_t)pos[v] + 2] = indptr[v];
   }
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_build_small(
     auto starts = [&](int v) {
       if (v == 0 || (v % kRangeRows) == 0) return true;
       const int b = (int)ip[v], a = (int)ip[v - 1], c = (int)ip[v + 1];
-      return (c - b > kHubThreshold) || (b - a > kHubThreshold) || (b / kRangeEdges != a / kRangeEdges);
+      return (c - b > kHubThreshold) || (b - a > kHubThreshold) || (b / kRangeEdgesSmall != a / kRangeEdgesSmall);
     };
     for (int v = tid; v < N; v += kSmallThreads) fa[v] = starts(v) ? 1u : 0u;
     __syncthreads();
@@ -465,7 +465,7 @@ using namespace stag;
 extern "C" int64_t stag_csx_items_capacity(int64_t num_edges, int64_t num_nodes) {
   // one item per started block of kRangeEdges edge positions and of kRangeRows rows, plus up to three
   // around every hub row
-  return num_edges / kRangeEdges + num_nodes / kRangeRows + 3 * (num_edges / (kHubThreshold + 1)) + 4;
+  return num_edges / range_edges_for(num_edges) + num_nodes / kRangeRows + 3 * (num_edges / (kHubThreshold + 1)) + 4;
 }
 
 extern "C" size_t stag_csx_workspace_bytes(int64_t num_edges, int64_t num_nodes) {
@@ -574,11 +574,11 @@ extern "C" int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t E,
   if (items && N > 0) {
     const int tb = 256;
     const unsigned gb = (unsigned)((N + tb - 1) / tb);
-    k_range_flags<<<gb, tb, 0, stream>>>(indptr, N, w.flags_a);
+    k_range_flags<<<gb, tb, 0, stream>>>(indptr, N, range_edges_for(E), w.flags_a);
     STAG_LAUNCH_CHECK();
     k_exclusive_scan<<<1, 1024, 0, stream>>>(w.flags_a, N, w.totals + 2);
     STAG_LAUNCH_CHECK();
-    k_range_scatter<<<gb, tb, 0, stream>>>(indptr, N, w.flags_a, items);
+    k_range_scatter<<<gb, tb, 0, stream>>>(indptr, N, range_edges_for(E), w.flags_a, items);
     STAG_LAUNCH_CHECK();
     k_range_close<<<gb, tb, 0, stream>>>(indptr, N, w.totals + 2, items);  // #items <= N
     STAG_LAUNCH_CHECK();
