@@ -168,7 +168,36 @@ def _fill_noise(spec, kind, K, p0, p1, ext, relu, in_norm, sample_base, seed, of
 
 
 def _c(t):
-    return None if t is None else t.detach().to(torch.float32).contiguous()
+    if t is None:
+        return None
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t.detach()
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already the current device (the context manager costs
+    several microseconds per call, which is what a small-graph launch is made of)."""
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == (dev.index or 0) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*a)
+
+
+def _workspace(st, lib, gstruct, by_dst, D, S):
+    """Scratch buffer of the graph, sized once per (orientation, D, S)."""
+    key = (by_dst, D, S)
+    cache = st.__dict__.setdefault("_ws_bytes", {})
+    if key not in cache:
+        cache[key] = lib.stag_spmm_workspace_bytes(ctypes.byref(gstruct), D, S)
+    return st.workspace(cache[key])
 
 
 class _NoiseEmit(torch.autograd.Function):
@@ -228,10 +257,9 @@ class _StochasticSpMM(torch.autograd.Function):
         ns = None
         if cfg["in_norm"]:
             ns = torch.empty((S, N, cfg["K"]), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             csc, _ = st.csx(True)
-            ws_bytes = lib.stag_spmm_workspace_bytes(ctypes.byref(csc), D, S)
-            ws = st.workspace(ws_bytes)
+            ws = _workspace(st, lib, csc, True, D, S)
             nz = _fill_noise(None, cfg["kind"], cfg["K"], p0c, p1c, extc, cfg["relu"], cfg["in_norm"],
                              cfg["sample_base"], cfg["seed"], cfg["offset"], cfg["param_shape"])
             _lib.check(lib.stag_spmm_fwd(
@@ -268,10 +296,9 @@ class _StochasticSpMM(torch.autograd.Function):
                     "StagLayer routes vi=True + norm=True through the emitted-noise path")
             gout = gout * ns  # d/d(sum) of s[v,c] * sum  (s constant w.r.t. x)
         dx = dp0 = dp1 = dext = None
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             csr, _ = st.csx(False)
-            ws_bytes = lib.stag_spmm_workspace_bytes(ctypes.byref(csr), D, S)
-            ws = st.workspace(ws_bytes)
+            ws = _workspace(st, lib, csr, False, D, S)
             if need_dx:
                 dx = torch.empty((S, N, D), dtype=torch.float32, device=dev)
 
