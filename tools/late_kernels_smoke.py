@@ -1,4 +1,4 @@
-"""Small invocations of the kernels added late in round 1 (compute-sanitizer target): both forms of the tensor-core
+"""Small invocations of the kernels added late in round 1 (a target for compute-sanitizer where the pool allows it): both forms of the tensor-core
 generator, the likelihood epilogue, the edge-parallel per-edge gradient kernel."""
 import os
 import sys
