@@ -1,6 +1,7 @@
-"""GPU check of the tensor-core noise path (STAG_NOISE_NORMAL_HADAMARD): emitted stream vs the numpy
-restatement, fused kernel vs the oracle fed the emitted noise, bitwise exactness of the tensor-core sums,
-and timings at the arxiv shape against the Box-Muller kernel."""
+"""GPU check of the tensor-core noise path (STAG_NOISE_NORMAL_HADAMARD): fused kernel vs a float64 torch aggregation
+fed the emitted noise, bitwise exactness of the tensor-core sums against the emitted stream, and timings at the arxiv
+shape against the Box-Muller kernel.  (The comparison of the emitted stream with its numpy restatement lives in
+tests/test_gpu_hadamard.py: only the tests use oracle/.)"""
 import os
 import sys
 import time
@@ -12,7 +13,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import stag_b200 as sb                      # noqa: E402
 from stag_b200.ops import NoiseSpec, stochastic_aggregate   # noqa: E402
-from oracle import ref_philox               # noqa: E402
 
 dev = torch.device("cuda", 0)
 
@@ -20,16 +20,6 @@ dev = torch.device("cuda", 0)
 def spec(p0, p1, K, E, **kw):
     t = lambda v: torch.as_tensor(v, dtype=torch.float32).to(dev)   # noqa: E731
     return NoiseSpec("normal", t(p0), t(p1), K, E, generator="hadamard", **kw)
-
-
-def check_emit():
-    for K in (128, 256):
-        E, seed, off = 777, 0xDEADBEEFCAFE, (7 << 32) + 5
-        sp = spec(1.0, 0.5, K, E, seed=seed, offset=off, sample_base=3)
-        w = sp.materialize(n_samples=2).cpu().numpy()
-        for s in range(2):
-            ref = ref_philox.noise("normal_hadamard", E, K, 3 + s, seed, off, 1.0, 0.5)
-            print("emit K=%d s=%d max|diff| %.3g  bitwise %s" % (K, s, np.abs(w[s] - ref).max(), np.array_equal(w[s], ref)))
 
 
 def dense_ref(src, dst, N, x, w, ss, ds):
@@ -112,9 +102,7 @@ def timing():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["emit", "exact", "fused", "timing"]
-    if "emit" in what:
-        check_emit()
+    what = sys.argv[1:] or ["exact", "fused", "timing"]
     if "exact" in what:
         check_exact()
     if "fused" in what:
