@@ -626,7 +626,9 @@ __global__ void __launch_bounds__(WH_THREADS, 2) agg_wh_stream_kernel(const AggP
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        // request the pass two ahead: (r, q + 2) or (r + 1, q - 2)
+        // request the pass two ahead: (r, q + 2) or (r + 1, q - 2); its ring slot was read by the whole group in the
+        // previous pass, hence the barrier
+        __syncwarp();
         if (q == 2) round_addresses(r + 1);
         const uint32_t ahead = slot >= 1 ? slot - 1 : 2;  // (slot + 2) % 3
         gather_pass(q < 2 ? r : r + 1, (q + 2) & 3, xring_s + ahead * WH_PASS_BYTES);
