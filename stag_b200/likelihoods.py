@@ -44,7 +44,7 @@ class Likelihood(torch.nn.Module, abc.ABC):
         if usable:
             from . import ops
             return ops.fused_nll(feats, y, mask, self.fused_kind)
-        return torch.stack([self.nll(feats[s], y, mask) for s in range(feats.shape[0])])
+        return torch.stack([self.nll(f, y, mask) for f in feats.unbind(0)])
 
 
 def _probs_likelihood(name, family, doc, fused_kind=None):

@@ -79,7 +79,8 @@ class StagModel(torch.nn.Module):
             elif h.dim() == feat.dim():
                 h = layer(graph, h)  # still sample-independent
             else:
-                h = torch.stack([layer(graph, h[s]) for s in range(n_samples)], dim=0)
+                # unbind, not h[s]: the backward of S selects is S zero-filled [S,N,D] tensors and S adds
+                h = torch.stack([layer(graph, hs) for hs in h.unbind(0)], dim=0)
         if h.dim() == feat.dim():
             h = h.unsqueeze(0).expand((n_samples,) + tuple(h.shape))
         return h
@@ -102,8 +103,8 @@ class StagModel(torch.nn.Module):
             total_nll = self.likelihood.nll_samples(outs, y, mask).sum()
         else:
             total_nll = 0.0
-            for s in range(n_samples):
-                nll = -self.likelihood.log_prob(outs[s], y)
+            for out_s in outs.unbind(0):
+                nll = -self.likelihood.log_prob(out_s, y)
                 if mask is not None:
                     nll = nll[mask]
                 total_nll = total_nll + nll.mean()
