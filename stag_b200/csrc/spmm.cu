@@ -33,6 +33,10 @@
 #include "common.cuh"
 #include "noise.cuh"
 
+#ifndef STAG_PACK2
+#define STAG_PACK2 1  // packed fp32 (FFMA2 / FMUL2) Box-Muller + accumulate in agg_stream_kernel
+#endif
+
 namespace stag {
 
 constexpr int AGG_THREADS = 256;
@@ -474,6 +478,39 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
           }
 #pragma unroll
           for (int g = 0; g < NB; ++g) {
+#if STAG_PACK2
+            if (KIND == STAG_NOISE_NORMAL) {
+              // Same arithmetic as the scalar branch below (every operation is one IEEE fp32 fma / mul), issued
+              // as packed FFMA2 / FMUL2 on register pairs: half the FMA-pipe instructions per variate.
+              const float2 AA = make_float2(A, A), BB = make_float2(B, B);
+              float2 wp[4];
+#pragma unroll
+              for (int ip = 0; ip < 2; ++ip) {
+                const uint32_t qa = q[4 * g + 2 * ip], qb = q[4 * g + 2 * ip + 1];
+                const float2 xl = make_float2(__uint_as_float(__byte_perm(qa, kf, 0x7610)),
+                                              __uint_as_float(__byte_perm(qb, kf, 0x7610)));
+                const float2 xh = make_float2(__uint_as_float(__byte_perm(qa, kf, 0x7632)),
+                                              __uint_as_float(__byte_perm(qb, kf, 0x7632)));
+                const float2 u1 = __ffma2_rn(xl, make_float2(1.52587890625e-05f, 1.52587890625e-05f),
+                                             make_float2(-127.99999237060547f, -127.99999237060547f));
+                const float2 ang = __ffma2_rn(xh, make_float2(9.58738019107841e-05f, 9.58738019107841e-05f),
+                                              make_float2(-804.2476806640625f, -804.2476806640625f));
+                const float2 rb = __fmul2_rn(make_float2(mufu_sqrt(-mufu_lg2(u1.x)), mufu_sqrt(-mufu_lg2(u1.y))), BB);
+                wp[2 * ip] = __ffma2_rn(make_float2(mufu_cos(ang.x), mufu_sin(ang.x)), make_float2(rb.x, rb.x), AA);
+                wp[2 * ip + 1] = __ffma2_rn(make_float2(mufu_cos(ang.y), mufu_sin(ang.y)), make_float2(rb.y, rb.y), AA);
+              }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int jq = 2 * g + h;
+                const float4 x4 = lds128f(slot_s + (uint32_t)jq * 512u);
+                float* a4 = acc + 4 * jq;
+                const float2 r0 = __ffma2_rn(wp[2 * h], make_float2(x4.x, x4.y), make_float2(a4[0], a4[1]));
+                const float2 r1 = __ffma2_rn(wp[2 * h + 1], make_float2(x4.z, x4.w), make_float2(a4[2], a4[3]));
+                a4[0] = r0.x; a4[1] = r0.y; a4[2] = r1.x; a4[3] = r1.y;
+              }
+              continue;
+            }
+#endif
             float w[8], kept[INNORM ? 8 : 1];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
