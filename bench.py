@@ -406,6 +406,17 @@ def run_ours(args, rank, world):
             "share_of_step": tot[dom] / sum(tot.values()),
             "per_class_ms": {k: float(np.mean(v)) for k, v in per.items()},
             "whole_step_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+    if path.normal_kind == path._lib.NOISE_NORMAL:
+        # Secondary ceiling: the launch draws E*S*D normals; Box-Muller needs 2 MUFU per normal and the
+        # XU pipe runs 16 lanes / clk / SM (measured, profiles/r01_microbench.txt), at the SM clock sampled during the run.
+        prop = torch.cuda.get_device_properties(dev)
+        mhz = (clocks or {}).get("sm_mhz") or getattr(prop, "clock_rate", 0) / 1e3
+        normals = float(N_EDGES) * S * WIDTH
+        if mhz:
+            xu_peak = prop.multi_processor_count * 16.0 * mhz * 1e6 / 2.0
+            roof["rng_ceiling"] = {"normals_per_launch": normals, "achieved_normals_per_s": normals / (avg_ms * 1e-3),
+                                   "xu_peak_normals_per_s": xu_peak, "frac": normals / (avg_ms * 1e-3) / xu_peak,
+                                   "note": "Box-Muller, 2 MUFU per normal, 16 MUFU lanes/clk/SM measured"}
     prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:

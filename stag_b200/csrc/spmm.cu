@@ -527,8 +527,14 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
                 w[2 * i] = fmaf(mufu_cos(ang), rb, A);
                 w[2 * i + 1] = fmaf(mufu_sin(ang), rb, A);
               } else if (KIND == STAG_NOISE_UNIFORM) {  // (A, B) carry the half -> uniform conversion
+#if STAG_PACK2
+                const float2 w2 = __ffma2_rn(make_float2(xl, xh), make_float2(B, B), make_float2(A, A));
+                w[2 * i] = w2.x;
+                w[2 * i + 1] = w2.y;
+#else
                 w[2 * i] = fmaf(xl, B, A);
                 w[2 * i + 1] = fmaf(xh, B, A);
+#endif
               } else {  // A = 2^23 + ceil(65536 p)
                 const bool k0 = xl < A, k1 = xh < A;
                 w[2 * i] = k0 ? B : 0.f;
@@ -544,10 +550,16 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
               const int jq = 2 * g + h;
               const float4 x4 = lds128f(slot_s + (uint32_t)jq * 512u);
               float* a4 = acc + 4 * jq;
+#if STAG_PACK2
+              const float2 r0 = __ffma2_rn(make_float2(w[4 * h], w[4 * h + 1]), make_float2(x4.x, x4.y), make_float2(a4[0], a4[1]));
+              const float2 r1 = __ffma2_rn(make_float2(w[4 * h + 2], w[4 * h + 3]), make_float2(x4.z, x4.w), make_float2(a4[2], a4[3]));
+              a4[0] = r0.x; a4[1] = r0.y; a4[2] = r1.x; a4[3] = r1.y;
+#else
               a4[0] = fmaf(w[4 * h + 0], x4.x, a4[0]);
               a4[1] = fmaf(w[4 * h + 1], x4.y, a4[1]);
               a4[2] = fmaf(w[4 * h + 2], x4.z, a4[2]);
               a4[3] = fmaf(w[4 * h + 3], x4.w, a4[3]);
+#endif
               if (INNORM && t + j < nedges) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) cntw[INNORM ? 4 * jq + i : 0] += kept[INNORM ? 4 * h + i : 0];
@@ -804,6 +816,34 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
           for (int g = 0; g < NB; ++g) {
             const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
             const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
+#if STAG_PACK2
+            // same operations as the scalar loop below, two words at a time on FFMA2 / FMUL2
+#pragma unroll
+            for (int ip = 0; ip < 2; ++ip) {
+              const uint32_t qa = q[2 * ip], qb = q[2 * ip + 1];
+              const float2 xl = make_float2(__uint_as_float(__byte_perm(qa, kf, 0x7610)),
+                                            __uint_as_float(__byte_perm(qb, kf, 0x7610)));
+              const float2 xh = make_float2(__uint_as_float(__byte_perm(qa, kf, 0x7632)),
+                                            __uint_as_float(__byte_perm(qb, kf, 0x7632)));
+              float2 ra, rb2;
+              if (KIND == STAG_NOISE_NORMAL) {
+                const float2 u1 = __ffma2_rn(xl, make_float2(1.52587890625e-05f, 1.52587890625e-05f),
+                                             make_float2(-127.99999237060547f, -127.99999237060547f));
+                const float2 ang = __ffma2_rn(xh, make_float2(9.58738019107841e-05f, 9.58738019107841e-05f),
+                                              make_float2(-804.2476806640625f, -804.2476806640625f));
+                const float rad0 = mufu_sqrt(-mufu_lg2(u1.x)), rad1 = mufu_sqrt(-mufu_lg2(u1.y));
+                ra = __fmul2_rn(make_float2(mufu_cos(ang.x), mufu_sin(ang.x)), make_float2(rad0, rad0));
+                rb2 = __fmul2_rn(make_float2(mufu_cos(ang.y), mufu_sin(ang.y)), make_float2(rad1, rad1));
+              } else {
+                const float2 k = make_float2(1.52587890625e-05f, 1.52587890625e-05f), o = make_float2(-128.0f, -128.0f);
+                ra = __ffma2_rn(make_float2(xl.x, xh.x), k, o);
+                rb2 = __ffma2_rn(make_float2(xl.y, xh.y), k, o);
+              }
+              raw[8 * g + 4 * ip] = ra.x; raw[8 * g + 4 * ip + 1] = ra.y;
+              raw[8 * g + 4 * ip + 2] = rb2.x; raw[8 * g + 4 * ip + 3] = rb2.y;
+            }
+            continue;
+#endif
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float xl = __uint_as_float(__byte_perm(q[i], kf, 0x7610));
@@ -826,6 +866,24 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
           const float4 x4 = lds128f(slot_s + (uint32_t)jq * 512u);
           xv[4 * jq] = x4.x; xv[4 * jq + 1] = x4.y; xv[4 * jq + 2] = x4.z; xv[4 * jq + 3] = x4.w;
         }
+#if STAG_PACK2
+        if (BODY == 0) {
+#pragma unroll
+          for (int i = 0; i < NA; i += 2) {
+            float2 y = __fmul2_rn(make_float2(xv[i], xv[i + 1]), make_float2(A, A));
+            const float2 r2 = make_float2(raw[i], raw[i + 1]);
+            if (p.relu) {
+              const float2 t2 = __ffma2_rn(r2, make_float2(P1[NB == 1 ? i : 0], P1[NB == 1 ? i + 1 : 0]),
+                                           make_float2(P0[NB == 1 ? i : 0], P0[NB == 1 ? i + 1 : 0]));
+              if (!(t2.x > 0.f)) y.x = 0.f;
+              if (!(t2.y > 0.f)) y.y = 0.f;
+            }
+            const float2 s0 = __fadd2_rn(make_float2(a0[i], a0[i + 1]), y);
+            const float2 s1 = __ffma2_rn(r2, y, make_float2(a1[i], a1[i + 1]));
+            a0[i] = s0.x; a0[i + 1] = s0.y; a1[i] = s1.x; a1[i + 1] = s1.y;
+          }
+        } else
+#endif
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
           if (BODY == 1) {
