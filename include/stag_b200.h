@@ -228,7 +228,7 @@ STAG_API int stag_gemm_tcgen05(const float* a, int64_t lda, const float* wt, int
                       const float* row_scale, const float* bias, int act,
                       float* out, int64_t ldo, void* ws, size_t ws_bytes, void* stream);
 
-/* Host-buffer convenience entry point (what bench.py's e2e leg and a non-torch caller use):
+/* Host-buffer convenience entry point for a non-torch caller (bench.py's e2e leg goes through the Python API instead):
  * COO graph, features and upstream gradient in HOST memory; builds CSC+CSR on the device,
  * runs forward + backward for S samples with generated noise and copies out / dx back.
  * Synchronous.  device = CUDA ordinal. */
