@@ -508,8 +508,9 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
                 const float2 r1 = __ffma2_rn(wp[2 * h + 1], make_float2(x4.z, x4.w), make_float2(a4[2], a4[3]));
                 a4[0] = r0.x; a4[1] = r0.y; a4[2] = r1.x; a4[3] = r1.y;
               }
-              continue;
-            }
+            } else {
+#else
+            {
 #endif
             float w[8], kept[INNORM ? 8 : 1];
 #pragma unroll
@@ -565,6 +566,7 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
                 for (int i = 0; i < 4; ++i) cntw[INNORM ? 4 * jq + i : 0] += kept[INNORM ? 4 * h + i : 0];
               }
             }
+            }  // scalar / non-Normal branch
           }
           if (INNORM && t + j < nedges) ++row_edges;
           if (ef < 0 && t + j < rowlim) {  // last edge of a row: write it, start the next one
@@ -842,8 +844,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
               raw[8 * g + 4 * ip] = ra.x; raw[8 * g + 4 * ip + 1] = ra.y;
               raw[8 * g + 4 * ip + 2] = rb2.x; raw[8 * g + 4 * ip + 3] = rb2.y;
             }
-            continue;
-#endif
+#else
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float xl = __uint_as_float(__byte_perm(q[i], kf, 0x7610));
@@ -858,6 +859,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
                 raw[8 * g + 2 * i + 1] = fmaf(xh, 1.52587890625e-05f, -128.0f);
               }
             }
+#endif
           }
         }
         float xv[NA];
