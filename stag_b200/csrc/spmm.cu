@@ -1649,6 +1649,7 @@ __global__ void emit_wh_kernel(const AggParams p, float* __restrict__ w_out, flo
 
 }  // namespace stag
 #include "spmm_tc.cuh"
+#include "spmm_wq.cuh"
 namespace stag {
 
 // Philox blocks needed by `width` channels: 8 per whole 64-channel group, one per started quad of
@@ -1997,7 +1998,10 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
       // the stream items), 1 = channel per thread
       static const char* form = getenv("STAG_TC_FORM");
       if ((form && atoi(form) == 1) || !g->items) return launch_tc(p, stream);
-      rc = launch_wh_stream(p, stream);
+      // 3 (default) = four lanes per stream reading z in their own layout, 256-bit gathers: 32-byte aligned rows
+      const bool a32 = (((uintptr_t)x | (uintptr_t)out) & 31) == 0 && ldx % 8 == 0 && ldo % 8 == 0 &&
+                       x_sample_stride % 8 == 0 && out_sample_stride % 8 == 0;
+      rc = ((form && atoi(form) == 2) || !a32) ? launch_wh_stream(p, stream) : launch_wh_quad(p, stream);
       if (rc) return rc;
       if (g->num_hubs > 0) {
         const int64_t total = (int64_t)S * g->num_hubs * D;
