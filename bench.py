@@ -425,6 +425,14 @@ def run_ours(args, rank, world):
     e2e_s, h2d, d2h = e2e_leg(dev, src, dst, S, rank * S, max(3, min(args.steps, 8)), 5, dist, args.normal)
     e2e = {"value": edge_samples / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "api": "stag_b200.ops.stochastic_aggregate + autograd, pinned host X in / dX + objective out every step, copies double-buffered on two copy streams"}
+    multi = None
+    if world > 1 and not args.no_multi:
+        # every number in here has a collective inside its timed region (bench_multi.py): strong scaling over the MC
+        # samples with the gradient / MC-mean all-reduces, PPI minibatch data parallel, row-partitioned products graph
+        import bench_multi
+        path.act = path.gbuf = path.gout = path.dx0 = None   # the headline's buffers (7 GB) make room for the legs
+        torch.cuda.empty_cache()
+        multi = bench_multi.run_all(dev, dist, rank, world, args.steps, args.warmup, args.normal)
     if rank != 0:
         return
     cpu = cpu_baseline(args.mode) if (world == 1 and not args.no_cpu_baseline) else None
@@ -438,6 +446,8 @@ def run_ours(args, rank, world):
                        "l2": "per-launch inputs (1.39 GB activations per layer) exceed the 126 MB L2; "
                              "layer-1 X (87 MB) is deliberately L2-resident across its 16 samples"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    if multi is not None:
+        line["multi_gpu"] = multi
     print(json.dumps(line), flush=True)
 
 
@@ -449,6 +459,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="mle", choices=["mle", "vi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the multi_gpu legs (collectives inside the timed region)")
     ap.add_argument("--normal", default="boxmuller", choices=["hadamard", "boxmuller"],
                     help="standard-normal generator of the fused kernels: tensor-core Walsh-Hadamard mix "
                          "(agg_tc_kernel) or 16-bit Box-Muller (agg_stream_kernel)")

@@ -59,13 +59,18 @@ __global__ void __launch_bounds__(NLL_THREADS) nll_kernel(const NllParams p) {
         for (int c = lane; c < p.C; c += 32) sum += row[c];
         sum = warp_sum(sum);
         const int64_t yv = p.y_idx[v];
-        const float py = row[yv];
+        // a label outside [0, C) (an ignore index on an unmasked row) is never dereferenced: the row's loss is NaN and
+        // its gradient zero, so the mistake is visible instead of an out-of-bounds read
+        const bool bad = yv < 0 || yv >= p.C;
+        const float py = bad ? __int_as_float(0x7fc00000) : row[yv];
         const float q = py / sum;
-        const float qc = fminf(fmaxf(q, kProbEps), 1.0f - kProbEps);
+        // torch: Categorical(probs=...) renormalises and clamps; a row that sums to zero (or is NaN) gives NaN there,
+        // and fmaxf / fminf would silently turn it into a finite value here
+        const float qc = (q != q || !(sum > 0.f)) ? __int_as_float(0x7fc00000) : fminf(fmaxf(q, kProbEps), 1.0f - kProbEps);
         if (lane == 0) acc -= logf(qc);
         if (drow) {
           // -log(clamp(p_y / sum)): the clamp passes the gradient only inside (eps, 1 - eps)
-          const bool inside = q >= kProbEps && q <= 1.0f - kProbEps;
+          const bool inside = !bad && q >= kProbEps && q <= 1.0f - kProbEps;
           const float inv_sum = 1.0f / sum;
           for (int c = lane; c < p.C; c += 32) {
             float g = 0.f;

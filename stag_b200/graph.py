@@ -25,13 +25,16 @@ from . import _lib
 class _Structure:
     """COO edge list + lazily built device CSC/CSR, shared by all views of a graph."""
 
-    def __init__(self, src, dst, num_nodes, batch_num_nodes=None, batch_num_edges=None, eid_map=None):
+    def __init__(self, src, dst, num_nodes, batch_num_nodes=None, batch_num_edges=None, eid_map=None, num_src=None):
         # eid_map [E]: id under which each local edge draws its Philox noise / indexes an external
         # noise tensor (row-partitioned graphs keep the edge ids of the unpartitioned graph)
+        # num_src: rows of the gathered operand when they differ from the destination rows (the local
+        # piece of a row-partitioned graph: owned destinations x owned + halo sources); default = num_nodes
         self.eid_map = eid_map
         self.src = src
         self.dst = dst
         self.num_nodes = int(num_nodes)
+        self.num_src = self.num_nodes if num_src is None else int(num_src)
         self.num_edges = int(src.shape[0])
         self.batch_num_nodes = batch_num_nodes
         self.batch_num_edges = batch_num_edges
@@ -49,7 +52,8 @@ class _Structure:
         """(StagGraph ctypes struct, keep-alive tensors) for the CSC (by_dst) or CSR."""
         key = bool(by_dst)
         if key not in self._csx:
-            g, keep = build_csx(self.src, self.dst, self.num_nodes, key)
+            g, keep = build_csx(self.src, self.dst, self.num_nodes if key else self.num_src, key,
+                                num_cols=self.num_src if key else self.num_nodes)
             if self.eid_map is not None and self.num_edges:
                 m = self.eid_map.to(device=self.device, dtype=torch.int32)
                 keep["eid"].copy_(m[keep["eid"].long()])
@@ -66,7 +70,7 @@ class _Structure:
                 self._deg[key] = (indptr[1:] - indptr[:-1]).to(torch.int64)
             else:
                 idx = self.dst if in_deg else self.src
-                self._deg[key] = torch.bincount(idx, minlength=self.num_nodes)
+                self._deg[key] = torch.bincount(idx, minlength=self.num_nodes if in_deg else self.num_src)
         return self._deg[key]
 
     def scale(self, in_deg, kind):
@@ -104,8 +108,9 @@ class _Structure:
         return self._ws
 
 
-def build_csx(src, dst, num_nodes, by_dst):
-    """Run ``stag_csx_build`` on the current stream.  Returns (StagGraph, tensors)."""
+def build_csx(src, dst, num_nodes, by_dst, num_cols=None):
+    """Run ``stag_csx_build`` on the current stream.  Returns (StagGraph, tensors).  `num_nodes` = rows of the
+    compressed structure (destinations for the CSC, sources for the CSR), `num_cols` = rows of the gathered operand."""
     if src.device.type != "cuda":
         raise _lib.StagLibraryError(
             "stag_b200: graph structure must live on a CUDA device (got %s); there is no CPU path"
@@ -136,7 +141,7 @@ def build_csx(src, dst, num_nodes, by_dst):
             hub_rows.data_ptr(), hub_seg_ptr.data_ptr(), row_order.data_ptr(), items.data_ptr(), erow.data_ptr(), eidf.data_ptr(), counts,
             ws.data_ptr(), ws_bytes, stream))
     g = _lib.StagGraph()
-    g.num_rows, g.num_cols, g.num_edges = N, N, E
+    g.num_rows, g.num_cols, g.num_edges = N, (N if num_cols is None else int(num_cols)), E
     g.indptr, g.indices, g.eid = indptr.data_ptr(), indices.data_ptr(), eid.data_ptr()
     g.num_hubs, g.num_hub_segs = int(counts[0]), int(counts[1])
     g.hub_rows, g.hub_seg_ptr = hub_rows.data_ptr(), hub_seg_ptr.data_ptr()
@@ -161,13 +166,13 @@ class Graph:
 
     is_block = False
 
-    def __init__(self, src=None, dst=None, num_nodes=None, _structure=None, eid_map=None):
+    def __init__(self, src=None, dst=None, num_nodes=None, _structure=None, eid_map=None, num_src=None):
         if _structure is None:
             src = torch.as_tensor(src, dtype=torch.int64)
             dst = torch.as_tensor(dst, dtype=torch.int64).to(src.device)
             if num_nodes is None:
                 num_nodes = int(max(src.max().item(), dst.max().item())) + 1 if src.numel() else 0
-            _structure = _Structure(src, dst, num_nodes, eid_map=eid_map)
+            _structure = _Structure(src, dst, num_nodes, eid_map=eid_map, num_src=num_src)
         self._s = _structure
         self.ndata = {}
         self.edata = {}
@@ -203,10 +208,12 @@ class Graph:
     def number_of_nodes(self):
         return self._s.num_nodes
 
+    def number_of_src_nodes(self):
+        return self._s.num_src
+
     num_nodes = number_of_nodes
-    number_of_src_nodes = number_of_nodes
     number_of_dst_nodes = number_of_nodes
-    num_src_nodes = number_of_nodes
+    num_src_nodes = number_of_src_nodes
     num_dst_nodes = number_of_nodes
 
     def number_of_edges(self):
@@ -243,7 +250,7 @@ class Graph:
             s = self._s
         else:
             s = _Structure(self._s.src.to(device), self._s.dst.to(device), self._s.num_nodes,
-                           self._s.batch_num_nodes, self._s.batch_num_edges, self._s.eid_map)
+                           self._s.batch_num_nodes, self._s.batch_num_edges, self._s.eid_map, self._s.num_src)
         g = Graph(_structure=s)
         g.ndata = {k: v.to(device) for k, v in self.ndata.items()}
         g.edata = {k: v.to(device) for k, v in self.edata.items()}

@@ -11,6 +11,7 @@ the noise in one pass and regenerates it in the backward.  Base layers that are 
 fused, and the vi+norm combination, receive a real tensor emitted from the same Philox
 stream (``stag_noise_emit``), so both routes see identical noise.
 """
+import weakref
 from typing import Union
 
 import torch
@@ -33,6 +34,18 @@ def _in_norm(graph, edge_weight_sample):
         torch.ne(current_sum, 0.0), desired_sum / current_sum, torch.ones_like(current_sum))
     _, dst = graph.edges()
     return edge_weight_sample * node_scaling[dst]
+
+
+class _GraphRef:
+    """Weak reference to the STRUCTURE of the last forward's graph (the local_var view itself dies with the call)."""
+
+    def __init__(self, graph):
+        self._ref = weakref.ref(graph._s)
+
+    def __call__(self):
+        from .graph import Graph
+        s = self._ref()
+        return None if s is None else Graph(_structure=s)
 
 
 class StagLayer(torch.nn.Module):
@@ -74,6 +87,18 @@ class StagLayer(torch.nn.Module):
         self.vi = vi
         self._noise_spec = None
         self._noise_tensor = None
+        self._graph_ref = None
+
+    # transient per-forward state (last graph, lazy noise) is not part of the module: it holds device structure
+    # (ctypes structs with pointers) and [E,K] tensors, so it is dropped on pickling / deepcopy
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_noise_spec"] = state["_noise_tensor"] = state["_graph_ref"] = None
+        return state
+
+    @property
+    def _last_graph(self):
+        return None if self._graph_ref is None else self._graph_ref()
 
     # the sample of the last forward, materialised on demand (stag/layers.py:107)
     @property
@@ -82,7 +107,11 @@ class StagLayer(torch.nn.Module):
             spec = self._noise_spec
             w = spec.materialize()
             if spec.in_norm:
-                w = _in_norm(self._last_graph, w)
+                g = self._last_graph
+                if g is None:
+                    raise RuntimeError("the graph of the last forward is gone: _edge_weight_sample with norm=True "
+                                       "must be read while that graph is alive")
+                w = _in_norm(g, w)
             self._noise_tensor = w
         return self._noise_tensor
 
@@ -122,7 +151,7 @@ class StagLayer(torch.nn.Module):
         S = 1 if n_samples is None else int(n_samples)
         spec = self.noise_spec(graph, sample_dimension, n_samples=S, sample_base=sample_base,
                                batched=n_samples is not None)
-        self._last_graph = graph
+        self._graph_ref = _GraphRef(graph)
         self._noise_tensor = None
         self._noise_spec = spec
 

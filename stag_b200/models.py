@@ -58,6 +58,10 @@ class StagModel(torch.nn.Module):
             if isinstance(layer, StagLayer):
                 if not getattr(layer.base_layer, "accepts_noise_spec", False):
                     return False
+                # a base layer must say that it takes [S,N,D] features with a sample-batched NoiseSpec
+                # (GatedGCN takes a NoiseSpec but runs its BatchNorm per pass: sequential passes, as the reference)
+                if not getattr(layer.base_layer, "accepts_sample_batch", False):
+                    return False
                 if layer.q_a.__class__.__name__ == "AmortizedDistribution":
                     return False
                 if layer.q_a.fused_parameters() is None or (layer.norm and layer.vi):
@@ -85,19 +89,21 @@ class StagModel(torch.nn.Module):
             h = h.unsqueeze(0).expand((n_samples,) + tuple(h.shape))
         return h
 
-    def forward(self, graph, feat, n_samples=1, return_parameters=False):
+    def forward(self, graph, feat, n_samples=1, return_parameters=False, sample_base=0):
         """Monte-Carlo predictive: mean of the outputs of ``n_samples`` stochastic passes,
-        then (unless ``return_parameters``) a sample from the likelihood (stag/models.py:45-61)."""
-        feat = self._forward_samples(graph, feat, n_samples).mean(dim=0)
+        then (unless ``return_parameters``) a sample from the likelihood (stag/models.py:45-61).
+        ``sample_base`` (extension): global index of this call's first Monte-Carlo sample -- ranks that shard the S
+        samples of one predictive pass ``sample_base = parallel.shard_samples(S, rank, world)[0]`` and a common seed."""
+        feat = self._forward_samples(graph, feat, n_samples, sample_base=sample_base).mean(dim=0)
         if return_parameters is True:
             return feat
         return self.likelihood.condition(feat).sample()
 
-    def loss_terms(self, graph, feat, y, mask=None, n_samples=1, kl_scaling=None):
+    def loss_terms(self, graph, feat, y, mask=None, n_samples=1, kl_scaling=None, sample_base=0):
         """(mean NLL, kl_scaling * mean KL) over ``n_samples`` passes (stag/models.py:63-84)."""
         if kl_scaling is None:
             kl_scaling = self.kl_scaling
-        outs = self._forward_samples(graph, feat, n_samples)
+        outs = self._forward_samples(graph, feat, n_samples, sample_base=sample_base)
         if hasattr(self.likelihood, "nll_samples"):
             # all samples in one fused pass on CUDA (stag_nll), torch.distributions otherwise
             total_nll = self.likelihood.nll_samples(outs, y, mask).sum()
@@ -118,8 +124,9 @@ class StagModel(torch.nn.Module):
         total_reg = reg * kl_scaling
         return total_nll, total_reg
 
-    def loss(self, graph, feat, y, mask=None, n_samples=1, kl_scaling=None):
-        nll, reg = self.loss_terms(graph, feat, y, mask=mask, n_samples=n_samples, kl_scaling=kl_scaling)
+    def loss(self, graph, feat, y, mask=None, n_samples=1, kl_scaling=None, sample_base=0):
+        nll, reg = self.loss_terms(graph, feat, y, mask=mask, n_samples=n_samples, kl_scaling=kl_scaling,
+                                   sample_base=sample_base)
         return nll + reg
 
 

@@ -250,7 +250,7 @@ class _StochasticSpMM(torch.autograd.Function):
         _require_cuda(feat, "feat")
         lib = _lib.load()
         S, shared = cfg["S"], cfg["shared"]
-        N, D = st.num_nodes, feat.shape[-1]
+        N, NS, D = st.num_nodes, st.num_src, feat.shape[-1]  # destination rows, rows of the gathered operand
         x = _c(feat)
         p0c, p1c, extc = _c(p0), _c(p1), _c(ext)
         out = torch.empty((S, N, D), dtype=torch.float32, device=dev)
@@ -263,7 +263,7 @@ class _StochasticSpMM(torch.autograd.Function):
             nz = _fill_noise(None, cfg["kind"], cfg["K"], p0c, p1c, extc, cfg["relu"], cfg["in_norm"],
                              cfg["sample_base"], cfg["seed"], cfg["offset"], cfg["param_shape"])
             _lib.check(lib.stag_spmm_fwd(
-                ctypes.byref(csc), x.data_ptr(), D, 0 if shared else N * D, D, S, ctypes.byref(nz),
+                ctypes.byref(csc), x.data_ptr(), D, 0 if shared else NS * D, D, S, ctypes.byref(nz),
                 _ptr(cfg["src_scale"]), _ptr(cfg["dst_scale"]), out.data_ptr(), D, N * D,
                 _ptr(ns), ws.data_ptr(), ws.numel(), _stream(dev)))
         ctx.cfg = cfg
@@ -283,7 +283,7 @@ class _StochasticSpMM(torch.autograd.Function):
         lib = _lib.load()
         dev = gout.device
         S, shared = cfg["S"], cfg["shared"]
-        N, D, K = st.num_nodes, gout.shape[-1], cfg["K"]
+        N, NS, D, K = st.num_nodes, st.num_src, gout.shape[-1], cfg["K"]
         need_dx = ctx.needs_input_grad[0]
         need_dp = (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and cfg["kind"] in (
             _lib.NOISE_NORMAL, _lib.NOISE_UNIFORM)
@@ -300,7 +300,7 @@ class _StochasticSpMM(torch.autograd.Function):
             csr, _ = st.csx(False)
             ws = _workspace(st, lib, csr, False, D, S)
             if need_dx:
-                dx = torch.empty((S, N, D), dtype=torch.float32, device=dev)
+                dx = torch.empty((S, NS, D), dtype=torch.float32, device=dev)
 
             def noise(sample_base, ext_slice=None):
                 return _fill_noise(None, cfg["kind"], K, p0c, p1c, extc if ext_slice is None else ext_slice,
@@ -313,7 +313,7 @@ class _StochasticSpMM(torch.autograd.Function):
                     nz = noise(cfg["sample_base"])
                     _lib.check(lib.stag_spmm_fwd(
                         ctypes.byref(csr), gout.data_ptr(), D, N * D, D, S, ctypes.byref(nz),
-                        _ptr(cfg["dst_scale"]), _ptr(cfg["src_scale"]), dx.data_ptr(), D, N * D,
+                        _ptr(cfg["dst_scale"]), _ptr(cfg["src_scale"]), dx.data_ptr(), D, NS * D,
                         0, ws.data_ptr(), ws.numel(), _stream(dev)))
             else:
                 edge_params = need_dp and cfg["param_shape"] >= _lib.PARAM_EDGE
@@ -333,10 +333,10 @@ class _StochasticSpMM(torch.autograd.Function):
                                None if extc is None else extc[s0:s0 + ns_])
                     xs = x if shared else x[s0:s0 + ns_]
                     _lib.check(lib.stag_spmm_bwd(
-                        ctypes.byref(csr), xs.data_ptr(), D, 0 if shared else N * D,
+                        ctypes.byref(csr), xs.data_ptr(), D, 0 if shared else NS * D,
                         gout[s0:s0 + ns_].data_ptr(), D, N * D, D, ns_, ctypes.byref(nz),
                         _ptr(cfg["src_scale"]), _ptr(cfg["dst_scale"]),
-                        0 if dx is None else dx[s0:s0 + ns_].data_ptr(), D, N * D,
+                        0 if dx is None else dx[s0:s0 + ns_].data_ptr(), D, NS * D,
                         _ptr(dp0), _ptr(dp1), 0 if dext is None else dext[s0:s0 + ns_].data_ptr(),
                         ws.data_ptr(), ws.numel(), _stream(dev)))
         gfeat = gp0 = gp1 = gext = None
@@ -381,8 +381,8 @@ def stochastic_aggregate(graph, feat, edge_weight=None, reduce="sum", src_scale=
             raise ValueError("feat has %d samples but n_samples=%s" % (S, n_samples))
     else:
         raise ValueError("feat must be [N,D] or [S,N,D]; got %s" % (tuple(feat.shape),))
-    if feat.shape[-2] != N:
-        raise ValueError("feat has %d rows, graph has %d nodes" % (feat.shape[-2], N))
+    if feat.shape[-2] != st.num_src:
+        raise ValueError("feat has %d rows, graph has %d source nodes" % (feat.shape[-2], st.num_src))
     D = feat.shape[-1]
     if reduce == "mean":
         m = st.scale(True, "inv")

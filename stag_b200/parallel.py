@@ -10,9 +10,10 @@ scripts/*/run.py ``model.cuda()``), so nothing here replaces a reference file.
                        gradient averaging with the same flat bucket.
 * rows of one graph -- 1-D block row partition of the destinations: rank r owns the in-edges
                        (CSC rows) of nodes [lo_r, hi_r) and the matching X row block.  Forward:
-                       all-gather of the X row blocks (halo), local aggregation into the owned
-                       rows.  Backward: local transposed aggregation gives a partial dX for ALL
-                       nodes, reduce-scatter(sum) returns each rank its block.
+                       halo exchange (only the source rows a rank's edges reference, one
+                       variable-size all-to-all), local aggregation into the owned rows.
+                       Backward: the partial gradients of the halo rows travel back to their
+                       owners along the same lists (`RowPartition`).
 """
 import torch
 import torch.distributed as dist
@@ -48,6 +49,34 @@ def allreduce_gradients(parameters, group=None, average=True):
     return flat.numel()
 
 
+class GradBucket:
+    """The gradients of `parameters` as views of ONE flat buffer, so that the all-reduce of a step is a single
+    collective on memory autograd has already written: no concatenation before it and no copies after it (the
+    per-parameter copies of ``allreduce_gradients`` cost 0.38 ms of a 2 ms PPI minibatch step, measured)."""
+
+    def __init__(self, parameters, group=None):
+        self.params = [p for p in parameters if p.requires_grad]
+        self.group = group
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else None
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            p.grad = self.flat[off:off + k].view_as(p)   # backward accumulates in place into the bucket
+            off += k
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self, average=True):
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if average:
+                self.flat /= dist.get_world_size(self.group)
+        return self.flat.numel()
+
+
 def mc_mean(local_sum, n_samples_total, group=None):
     """Monte-Carlo predictive mean from per-rank partial sums of the [N,C] outputs
     (stag/models.py:46-55 computes the mean of the stacked per-sample outputs)."""
@@ -63,31 +92,159 @@ def row_blocks(num_nodes, world):
     return [min(r * per, num_nodes) for r in range(world + 1)], per
 
 
+def _all_to_all_rows(out, inp, recv_counts, send_counts, group=None, async_op=False):
+    """Variable-size row exchange: rows [sum(send_counts[:q]), +send_counts[q]) of `inp` go to rank q, the rows
+    received from rank q land at [sum(recv_counts[:q]), +recv_counts[q]) of `out`.  NCCL: one
+    all_to_all_single; gloo (CPU tests) has no all-to-all: point-to-point pairs."""
+    if dist.get_backend(group) != "gloo":
+        return dist.all_to_all_single(out, inp, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts),
+                                      group=group, async_op=async_op)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    so = ro = 0
+    reqs = []
+    for q in range(world):
+        sv, rv = inp[so:so + send_counts[q]], out[ro:ro + recv_counts[q]]
+        if q == rank:
+            rv.copy_(sv)
+        else:
+            if send_counts[q]:
+                reqs.append(dist.isend(sv.contiguous(), q, group=group))
+            if recv_counts[q]:
+                reqs.append(("recv", rv, q))
+        so += send_counts[q]
+        ro += recv_counts[q]
+    for r in reqs:
+        if isinstance(r, tuple):
+            buf = torch.empty_like(r[1])
+            dist.recv(buf, r[2], group=group)
+            r[1].copy_(buf)
+    for r in reqs:
+        if not isinstance(r, tuple):
+            r.wait()
+    return None
+
+
 class RowPartition:
     """1-D row partition of one large graph over the ranks of `group`.
 
-    ``aggregate(graph, feat, edge_weight, src_scale, dst_scale, n_samples)`` is the local
-    operator (``stag_b200.ops.stochastic_aggregate`` on the GPU; the CPU tests inject the
-    oracle).  The local graph keeps GLOBAL source ids (it gathers from the all-gathered X)
-    and global destination ids restricted to the owned block, so edge ids -- and therefore the
-    Philox noise of every edge -- are those of the unpartitioned graph.
+    Rank r owns the destination rows [lo_r, hi_r) -- their in-edges and the matching X row block.  Two forms of the
+    feature exchange:
+
+    * ``halo=True`` (default): every rank receives ONLY the source rows its own edges reference.  The needed-row
+      lists are exchanged once (``setup_halo``); per layer ``exchange`` gathers the requested rows of the owned
+      block into a send buffer and moves them with one variable-size all-to-all (NCCL ``all_to_all_single``).
+      The local graph is bipartite: destinations = owned rows, sources = [owned rows | halo rows sorted by global
+      id] (``stag_b200.Graph(..., num_src=)``), so nothing is computed or stored for rows a rank does not own.
+      Backward: the partial gradients of the halo rows travel back along the same lists (``exchange_back``) and
+      are added into the owners' blocks -- the reduce-scatter of dX restricted to the rows that were used.
+    * ``halo=False``: all-gather of whole X row blocks / reduce-scatter of a full [N,D] partial dX (round 1).
+
+    Either way the local graph keeps the edge ids of the unpartitioned graph (``eid_map``): the Philox noise of every
+    edge, and the order in which a row's in-edges are summed, are those of the single-GPU run -- the forward is
+    bitwise identical.  ``aggregate(graph, feat, edge_weight, ...)`` is ``stag_b200.ops.stochastic_aggregate`` on
+    the GPU; the CPU tests inject the oracle.
     """
 
-    def __init__(self, src, dst, num_nodes, rank, world, group=None):
+    def __init__(self, src, dst, num_nodes, rank, world, group=None, halo=True):
         self.rank, self.world, self.group = rank, world, group
         self.num_nodes = int(num_nodes)
         self.bounds, self.per = row_blocks(num_nodes, world)
         self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.n_own = self.hi - self.lo
         own = (dst >= self.lo) & (dst < self.hi)
         self.edge_ids = torch.nonzero(own, as_tuple=False).reshape(-1)   # global edge ids, increasing
         self.src = src[own]
         self.dst = dst[own]
         self.padded = self.per * world
+        self.halo = bool(halo)
+        if self.halo:
+            self._plan_halo()
+
+    # ---- halo plan ------------------------------------------------------------------------------------------
+    def _plan_halo(self):
+        src = self.src
+        remote = (src < self.lo) | (src >= self.hi)
+        self.need = torch.unique(src[remote])            # sorted global ids: grouped by owner, increasing
+        owner = torch.div(self.need, self.per, rounding_mode="floor")
+        self.recv_counts = torch.bincount(owner, minlength=self.world).tolist()
+        self.n_halo = int(self.need.numel())
+        self.n_ext = self.n_own + self.n_halo
+        # extended source index: owned rows first, then the halo rows in `need` order
+        ext = torch.where(remote, self.n_own + torch.searchsorted(self.need, src), src - self.lo)
+        self.src_ext = ext
+        self.dst_loc = self.dst - self.lo
+        self.send_counts = None
+        self.send_idx = None
+
+    def setup_halo(self):
+        """Tell every owner which of its rows this rank needs (once per graph).  Collective."""
+        dev = self.need.device
+        if self.world == 1:
+            self.send_counts, self.send_idx = [0], torch.empty(0, dtype=torch.int64, device=dev)
+            return self
+        rc = torch.tensor(self.recv_counts, dtype=torch.int64, device=dev)
+        sc = torch.empty_like(rc)
+        if dist.get_backend(self.group) == "gloo":
+            got = [None] * self.world
+            dist.all_gather_object(got, self.recv_counts, group=self.group)
+            sc = torch.tensor([got[q][self.rank] for q in range(self.world)], dtype=torch.int64)
+        else:
+            dist.all_to_all_single(sc, rc, group=self.group)
+        self.send_counts = sc.tolist()
+        owner_lo = torch.tensor(self.bounds[:-1], dtype=torch.int64, device=dev)
+        owner = torch.div(self.need, self.per, rounding_mode="floor")
+        req = (self.need - owner_lo[owner]).contiguous()     # row indices inside the owner's block
+        self.send_idx = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=dev)
+        _all_to_all_rows(self.send_idx, req, self.send_counts, self.recv_counts, group=self.group)
+        return self
+
+    def halo_bytes(self, D, itemsize=4):
+        """(received, sent) bytes of one exchange of [*, D] rows."""
+        return self.n_halo * D * itemsize, int(sum(self.send_counts or [0])) * D * itemsize
 
     def local_graph(self, graph_cls):
-        """Local structure over all N nodes (only owned destinations have in-edges)."""
+        """Local structure: bipartite (owned destinations x owned + halo sources) with ``halo=True``, else over
+        all N nodes (only owned destinations have in-edges).  Edge ids are those of the unpartitioned graph."""
+        if self.halo:
+            return graph_cls(self.src_ext, self.dst_loc, self.n_own, eid_map=self.edge_ids, num_src=self.n_ext)
         return graph_cls(self.src, self.dst, self.num_nodes, eid_map=self.edge_ids)
 
+    def exchange(self, x_block, out=None, async_op=False):
+        """Owned rows [n_own, D] (or [S, n_own, D]) -> extended operand [n_ext, D] ([S, n_ext, D]): own rows, then
+        the halo rows received from their owners.  With ``async_op`` returns (x_ext, work); the collective runs on
+        the communicator's stream and the caller overlaps it with work that does not read the halo rows."""
+        lead = x_block.shape[:-2]
+        D = x_block.shape[-1]
+        if out is None:
+            out = torch.empty(lead + (self.n_ext, D), dtype=x_block.dtype, device=x_block.device)
+        out[..., : self.n_own, :].copy_(x_block)
+        if self.world == 1 or (self.n_halo == 0 and sum(self.send_counts) == 0):
+            return (out, None) if async_op else out
+        if len(lead) == 0:
+            send = x_block.index_select(0, self.send_idx)
+            recv = out[self.n_own:]
+            work = _all_to_all_rows(recv, send, self.recv_counts, self.send_counts, group=self.group, async_op=async_op)
+        else:   # [S, rows, D]: rows outermost on the wire so that one all-to-all moves every sample
+            S = lead[0]
+            send = x_block.index_select(1, self.send_idx).transpose(0, 1).contiguous().reshape(-1, S * D)
+            recv = torch.empty((self.n_halo, S * D), dtype=x_block.dtype, device=x_block.device)
+            work = _all_to_all_rows(recv, send, self.recv_counts, self.send_counts, group=self.group, async_op=False)
+            out[:, self.n_own:, :].copy_(recv.reshape(self.n_halo, S, D).transpose(0, 1))
+        return (out, work) if async_op else out
+
+    def exchange_back(self, dx_ext):
+        """Partial gradient of the extended operand [n_ext, D] -> gradient of the owned rows [n_own, D]: the halo
+        part travels back to the owners and is added there (index_add in peer order: deterministic)."""
+        D = dx_ext.shape[-1]
+        dx = dx_ext[: self.n_own].clone()
+        if self.world == 1:
+            return dx
+        back = torch.empty((int(sum(self.send_counts)), D), dtype=dx_ext.dtype, device=dx_ext.device)
+        _all_to_all_rows(back, dx_ext[self.n_own:].contiguous(), self.send_counts, self.recv_counts, group=self.group)
+        dx.index_add_(0, self.send_idx, back)
+        return dx
+
+    # ---- whole-block form (halo=False) --------------------------------------------------------------------------
     def gather_features(self, x_block):
         """all-gather of the owned X row blocks -> full X [N,D] (the halo exchange)."""
         D = x_block.shape[-1]

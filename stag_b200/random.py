@@ -3,40 +3,69 @@
 Every fused forward consumes one ``offset`` (the Philox call counter); the backward
 of that call regenerates the same noise from the saved (seed, offset).  This plays
 the role torch's global CUDA generator plays for the reference
-(``expand([E,K]).rsample()``, stag/layers.py:117-127): ``manual_seed`` makes a run
-reproducible, successive calls are independent.
+(``expand([E,K]).rsample()``, stag/layers.py:117-127):
+
+* the state is PROCESS-GLOBAL (one stream for all threads, like torch's default generator);
+* by default the seed follows torch's: it is ``torch.initial_seed()`` (non-deterministic unless
+  ``torch.manual_seed`` was called), and a later ``torch.manual_seed(k)`` restarts the stream at
+  (k, 0) -- so ``torch.manual_seed`` makes a run reproducible, as it does for the reference;
+* ``manual_seed(seed)`` sets the seed explicitly; ``fold_rank(rank)`` derives a per-rank stream
+  from the current seed (data-parallel ranks working on DIFFERENT minibatches; ranks sharding
+  the Monte-Carlo samples of ONE forward keep a common seed and differ in ``sample_base``);
+* ``get_state()`` / ``set_state()`` return / restore (seed, offset) for checkpoint / resume (the
+  state is deliberately not part of ``state_dict``: the reference's keys are kept).
 """
 import threading
 
-_state = threading.local()
+import torch
+
+_lock = threading.Lock()
+_state = {"seed": None, "offset": 0, "torch_seed": None, "explicit": False}
+_MASK = 0xFFFFFFFFFFFFFFFF
 
 
-def _st():
-    if not hasattr(_state, "seed"):
-        _state.seed = 0x5EED5EED
-        _state.offset = 0
-    return _state
+def _sync_with_torch():
+    """Called with the lock held: adopt torch's seed at first use and whenever torch is re-seeded."""
+    ts = int(torch.initial_seed()) & _MASK
+    if _state["seed"] is None or ts != _state["torch_seed"]:
+        _state["seed"], _state["offset"], _state["explicit"] = ts, 0, False
+    _state["torch_seed"] = ts
 
 
 def manual_seed(seed):
-    st = _st()
-    st.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    st.offset = 0
+    with _lock:
+        _state["seed"] = int(seed) & _MASK
+        _state["offset"] = 0
+        _state["explicit"] = True
+        _state["torch_seed"] = int(torch.initial_seed()) & _MASK
+
+
+def fold_rank(rank):
+    """Derive this rank's stream from the current seed (splitmix-style odd multiplier)."""
+    with _lock:
+        _sync_with_torch()
+        _state["seed"] = (_state["seed"] ^ ((int(rank) + 1) * 0x9E3779B97F4A7C15)) & _MASK
+        _state["offset"] = 0
+        _state["explicit"] = True
 
 
 def get_state():
-    st = _st()
-    return st.seed, st.offset
+    with _lock:
+        _sync_with_torch()
+        return _state["seed"], _state["offset"]
 
 
 def set_state(seed, offset):
-    st = _st()
-    st.seed, st.offset = int(seed), int(offset)
+    with _lock:
+        _state["seed"], _state["offset"] = int(seed) & _MASK, int(offset)
+        _state["explicit"] = True
+        _state["torch_seed"] = int(torch.initial_seed()) & _MASK
 
 
 def next_offset():
     """Reserve one Philox call counter and return (seed, offset)."""
-    st = _st()
-    off = st.offset
-    st.offset = off + 1
-    return st.seed, off
+    with _lock:
+        _sync_with_torch()
+        off = _state["offset"]
+        _state["offset"] = off + 1
+        return _state["seed"], off

@@ -10,6 +10,7 @@ from ..graph import as_graph
 
 class GatedGCN(nn.Module):
     accepts_noise_spec = True
+    accepts_sample_batch = False  # BatchNorm statistics are per pass: StagModel runs the samples sequentially
 
     def __init__(self, input_dim, output_dim, dropout=0.0, batch_norm=True, residual=False):
         super().__init__()

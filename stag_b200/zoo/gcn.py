@@ -21,6 +21,7 @@ class DGLError(Exception):
 
 class GCN(nn.Module):
     accepts_noise_spec = True
+    accepts_sample_batch = True   # [S,N,D] features with one sample-batched NoiseSpec (StagModel._can_batch)
 
     def __init__(self, in_feats, out_feats, norm="both", weight=True, bias=True, activation=None,
                  allow_zero_in_degree=False):

@@ -9,6 +9,7 @@ from ..graph import as_graph
 
 class GIN(nn.Module):
     accepts_noise_spec = True
+    accepts_sample_batch = True   # [S,N,D] features with one sample-batched NoiseSpec (StagModel._can_batch)
 
     def __init__(self, in_features, out_features, aggregator_type="sum", init_eps=0, learn_eps=False,
                  activation=None):

@@ -16,6 +16,7 @@ from ..graph import as_graph
 
 class GraphSAGE(nn.Module):
     accepts_noise_spec = True
+    accepts_sample_batch = True   # [S,N,D] features with one sample-batched NoiseSpec (StagModel._can_batch)
 
     def __init__(self, in_features, out_features, activation=None, aggregator_type="mean"):
         super().__init__()

@@ -176,3 +176,53 @@ def test_amortized_condition_equals_the_concatenated_form(out_features, hidden):
             assert torch.allclose(q.new_parameters[key], ref, rtol=1e-12, atol=1e-12)
         dist = q.base_distribution
         assert dist.loc.shape[-2:] == (E, out_features) and (dist.scale > 0).all()
+
+
+def test_philox_stream_follows_torch_seed_and_is_process_global():
+    """The default seed is torch's: torch.manual_seed restarts the stream, threads share one counter,
+    fold_rank separates data-parallel ranks, get_state / set_state resume it."""
+    import threading
+    import stag_b200 as sb
+    torch.manual_seed(1234)
+    assert sb.random.next_offset() == (1234, 0) and sb.random.next_offset() == (1234, 1)
+    torch.manual_seed(99)
+    assert sb.random.next_offset() == (99, 0)
+    got = []
+    t = threading.Thread(target=lambda: got.append(sb.random.next_offset()))
+    t.start(); t.join()
+    assert got == [(99, 1)]                       # one process-global counter, not one per thread
+    state = sb.random.get_state()
+    assert state == (99, 2)
+    sb.random.fold_rank(0)
+    s0 = sb.random.get_state()[0]
+    sb.random.set_state(*state)
+    sb.random.fold_rank(1)
+    s1 = sb.random.get_state()[0]
+    assert s0 != s1 and s0 != 99 and sb.random.get_state()[1] == 0
+    sb.random.set_state(*state)
+    assert sb.random.next_offset() == (99, 2)
+    sb.manual_seed(5)
+    assert sb.random.next_offset() == (5, 0)
+
+
+def test_model_api_carries_sample_base_and_layers_pickle():
+    import copy
+    import inspect
+    import pickle
+    import stag_b200 as sb
+    for fn in (sb.models.StagModel.forward, sb.models.StagModel.loss, sb.models.StagModel.loss_terms):
+        assert "sample_base" in inspect.signature(fn).parameters
+    layer = sb.layers.StagLayer(sb.zoo.GCN(4, 3))
+    g = sb.Graph(torch.tensor([0, 1]), torch.tensor([1, 0]), 2)
+    layer._graph_ref = sb.layers._GraphRef(g)       # what a forward leaves behind
+    layer._noise_tensor = torch.ones(2, 4)
+    clone = copy.deepcopy(layer)
+    assert clone._graph_ref is None and clone._noise_tensor is None
+    assert pickle.loads(pickle.dumps(layer)).base_layer.weight.shape == (4, 3)
+    assert layer._last_graph is not None
+    del g
+    assert layer._last_graph is None                 # weak: the layer does not keep graphs (and their CSC / CSR) alive
+    # GatedGCN runs the samples sequentially (per-pass BatchNorm statistics), the other fused layers batch them
+    assert sb.zoo.GCN.accepts_sample_batch and not sb.zoo.GatedGCN.accepts_sample_batch
+    m = sb.models.StagModel(torch.nn.ModuleList([sb.layers.StagLayer(sb.zoo.GatedGCN(4, 4))]))
+    assert m._can_batch() is False

@@ -39,6 +39,15 @@ def _worker(rank, world, port, ret):
         n = P.allreduce_gradients(lin.parameters())
         assert n == 15
         assert torch.allclose(lin.weight.grad, torch.full((3, 4), 2 * 1.5))
+        # --- the same through GradBucket: gradients are views of the flat buffer, no copies -----
+        lin2 = torch.nn.Linear(4, 3)
+        bucket = P.GradBucket(lin2.parameters())
+        for _ in range(2):   # second round: zero() really clears what backward accumulated
+            bucket.zero()
+            lin2(x).sum().backward()
+            assert bucket.allreduce() == 15
+            assert lin2.weight.grad.data_ptr() == bucket.flat.data_ptr()
+            assert torch.allclose(lin2.weight.grad, torch.full((3, 4), 2 * 1.5)) and torch.allclose(lin2.bias.grad, torch.full((3,), 2.0))
         # --- MC mean --------------------------------------------------------------------------
         m = P.mc_mean(torch.full((3, 2), float(rank + 1)) * 2, 4)
         assert torch.allclose(m, torch.full((3, 2), 1.5))
@@ -49,7 +58,7 @@ def _worker(rank, world, port, ret):
         X = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32))
         W = torch.from_numpy((1 + 0.3 * rng.standard_normal((E, D))).astype(np.float32))
         G = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32))
-        part = P.RowPartition(src, dst, N, rank, world)
+        part = P.RowPartition(src, dst, N, rank, world, halo=False)
         xfull = part.gather_features(X[part.lo:part.hi].clone()).requires_grad_(True)
         assert torch.equal(xfull.detach(), X)
         # local aggregation over the owned destinations, noise indexed by GLOBAL edge id
@@ -63,6 +72,22 @@ def _worker(rank, world, port, ret):
         assert torch.allclose(own.detach(), full.detach()[part.lo:part.hi], atol=1e-6)
         assert torch.allclose(dx_block, Xo.grad[part.lo:part.hi], atol=1e-5)
         assert out.detach()[: part.lo].abs().sum() == 0 and out.detach()[part.hi:].abs().sum() == 0
+        # --- halo form: only the referenced source rows travel, bipartite local graph ------------------------
+        hp = P.RowPartition(src, dst, N, rank, world).setup_halo()
+        assert hp.n_halo == len(set(hp.src.tolist()) - set(range(hp.lo, hp.hi))) and hp.n_ext == hp.n_own + hp.n_halo
+        xb = X[hp.lo:hp.hi].clone().requires_grad_(True)
+        x_ext = hp.exchange(xb.detach())
+        assert torch.equal(x_ext[: hp.n_own], X[hp.lo:hp.hi]) and torch.equal(x_ext[hp.n_own:], X[hp.need])
+        x_ext.requires_grad_(True)
+        out_h = ref_spmm.aggregate(hp.src_ext, hp.dst_loc, hp.n_ext, x_ext, W[hp.edge_ids])[: hp.n_own]
+        assert torch.equal(out_h.detach(), own.detach())        # same edges, same order: bitwise
+        out_h.backward(G[hp.lo:hp.hi])
+        dx_h = hp.exchange_back(x_ext.grad)
+        assert torch.allclose(dx_h, Xo.grad[hp.lo:hp.hi], atol=1e-5)
+        # sample-batched exchange [S, rows, D]
+        X3 = torch.stack([X, 2 * X])
+        x3 = hp.exchange(X3[:, hp.lo:hp.hi].contiguous())
+        assert torch.equal(x3[1, hp.n_own:], 2 * X[hp.need])
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

@@ -68,7 +68,7 @@ def main():
 
     # ---- 3: row partition ------------------------------------------------------------------------------------
     ts, td = torch.from_numpy(src), torch.from_numpy(dst)
-    part = P.RowPartition(ts, td, N, rank, world)
+    part = P.RowPartition(ts, td, N, rank, world, halo=False)
     lg = part.local_graph(stag.Graph).to("cuda")
     D = 64
     X = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32)).cuda()
@@ -85,12 +85,33 @@ def main():
     err_out = rel(out[part.lo:part.hi], full[part.lo:part.hi])
     err_dx = rel(dx_block, Xr.grad[part.lo:part.hi])
 
-    res = torch.tensor([max(errs.values()), err_mean, err_out, err_dx], device="cuda", dtype=torch.float64)
+    # ---- 4: row partition with a proper halo (only the referenced source rows travel; bipartite local graph) ----
+    hp = P.RowPartition(ts.cuda(), td.cuda(), N, rank, world).setup_halo()
+    hg = hp.local_graph(stag.Graph)
+    x_ext = hp.exchange(X[hp.lo:hp.hi].contiguous()).requires_grad_(True)
+    S = 3
+    spec_s = lambda e: stag.ops.NoiseSpec("normal", one, sg, D, e, seed=9, offset=1, n_samples=S, batched=True)  # noqa: E731
+    out_h = stag.ops.stochastic_aggregate(hg, x_ext, spec_s(hg.number_of_edges()), n_samples=S)     # [S, n_own, D]
+    G3 = torch.stack([G, 0.5 * G, -G])
+    out_h.backward(G3[:, hp.lo:hp.hi])
+    dx_h = hp.exchange_back(x_ext.grad)
+    Xs = X.clone().requires_grad_(True)
+    full_s = stag.ops.stochastic_aggregate(g, Xs, spec_s(E), n_samples=S)
+    full_s.backward(G3)
+    halo_bitwise = float(torch.equal(out_h, full_s[:, hp.lo:hp.hi]))
+    err_dx_h = rel(dx_h, Xs.grad[hp.lo:hp.hi])
+    recv_b, _ = hp.halo_bytes(D)
+    halo_frac = recv_b / float((world - 1) * hp.per * D * 4)
+
+    res = torch.tensor([max(errs.values()), err_mean, err_out, err_dx, err_dx_h, 1.0 - halo_bitwise, halo_frac],
+                       device="cuda", dtype=torch.float64)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:
         print("world=%d bucket=%d floats  max rel err: grads %.2e  mc-mean %.2e  row-partition out %.2e dx %.2e"
-              % (world, n_bucket, *res.tolist()))
-        ok = res[0] < 1e-4 and res[1] < 1e-5 and res[2] < 1e-6 and res[3] < 1e-5
+              % (world, n_bucket, *res.tolist()[:4]))
+        print("halo form: forward bitwise == unpartitioned: %s   dx rel err %.2e   halo rows received = %.0f%% of a full all-gather"
+              % ("yes" if res[5] == 0 else "NO", res[4], 100 * res[6]))
+        ok = res[0] < 1e-4 and res[1] < 1e-5 and res[2] < 1e-6 and res[3] < 1e-5 and res[4] < 1e-5 and res[5] == 0
         print("DDP CHECK", "OK" if ok else "FAILED")
     dist.destroy_process_group()
 
