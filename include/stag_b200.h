@@ -195,6 +195,29 @@ STAG_API int stag_spmm_bwd(const StagGraph* csr, const float* x, int64_t ldx, in
 STAG_API int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_t S,
                     float* w_out, float* eps_out, void* stream);
 
+/* Sample-based KL terms without the noise tensor: replaces the fallback of StagLayer.kl_divergence
+ * (stag/layers.py:139-141: q_a.log_prob(w).sum(-1).mean() - p_a.log_prob(w).sum(-1).mean() on the stored [E,K]
+ * sample, used when torch has no analytic KL, e.g. the mixture prior of
+ * scripts/citation_rec_contrastive/gcn/run.py:44-52).  The sample is regenerated from `noise` (the spec of the
+ * forward: same seed / offset / sample_base / relu) and reduced on the fly:
+ *   sums[0] = sum over (sample, edge, channel) of log q(w),  sums[1] = the same of log p(w)   (device, double[2])
+ *   dparam0 / dparam1 (optional, device, parameter shape of `noise`): d(sums[0] - sums[1]) / d(p0, p1), the
+ *   reparameterisation path w(p0, p1) included.  Deterministic (fixed summation order).
+ * q: STAG_NOISE_NORMAL (p0 loc, p1 scale) or STAG_NOISE_UNIFORM (low, high), no in_norm.  The prior is a handful of
+ * HOST scalars. */
+#define STAG_PRIOR_MAX_COMPONENTS 8
+#define STAG_PRIOR_NORMAL_MIXTURE 1
+typedef struct StagPrior {
+  int32_t kind;                              /* STAG_PRIOR_NORMAL_MIXTURE                                     */
+  int32_t M;                                 /* components: 1 = a plain Normal                                */
+  float weight[STAG_PRIOR_MAX_COMPONENTS];   /* mixture probabilities (normalised by the library)             */
+  float loc[STAG_PRIOR_MAX_COMPONENTS];
+  float scale[STAG_PRIOR_MAX_COMPONENTS];
+} StagPrior;
+STAG_API size_t stag_noise_kl_workspace_bytes(int32_t K);
+STAG_API int stag_noise_kl(const StagNoise* noise, int64_t num_edges, int32_t S, const StagPrior* prior, double* sums,
+                  float* dparam0, float* dparam1, void* ws, size_t ws_bytes, void* stream);
+
 /* Segmented readout over batch_num_nodes (SumNodes / MeanNodes, stag/layers.py:156-178):
  * out[b,c] = sum (or mean) of feat rows in [node_ptr[b], node_ptr[b+1]). */
 STAG_API int stag_segment_reduce(const float* feat, int64_t ldf, const int32_t* node_ptr, int32_t num_graphs,

@@ -50,6 +50,18 @@ class StagNoise(ctypes.Structure):
     ]
 
 
+PRIOR_MAX_COMPONENTS = 8
+PRIOR_NORMAL_MIXTURE = 1
+
+
+class StagPrior(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32), ("M", ctypes.c_int32),
+        ("weight", ctypes.c_float * PRIOR_MAX_COMPONENTS), ("loc", ctypes.c_float * PRIOR_MAX_COMPONENTS),
+        ("scale", ctypes.c_float * PRIOR_MAX_COMPONENTS),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/stag_b200.h one to one
 _V, _I, _I32, _I64, _SZ = ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
 _GP, _NP = ctypes.POINTER(StagGraph), ctypes.POINTER(StagNoise)
@@ -67,6 +79,8 @@ SIGNATURES = {
     "stag_spmm_bwd": (_I, [_GP, _V, _I64, _I64, _V, _I64, _I64, _I32, _I32, _NP, _V, _V, _V, _I64, _I64,
                            _V, _V, _V, _V, _SZ, _V]),
     "stag_noise_emit": (_I, [_NP, _I64, _I32, _V, _V, _V]),
+    "stag_noise_kl_workspace_bytes": (_SZ, [_I32]),
+    "stag_noise_kl": (_I, [_NP, _I64, _I32, ctypes.POINTER(StagPrior), _V, _V, _V, _V, _SZ, _V]),
     "stag_segment_reduce": (_I, [_V, _I64, _V, _I32, _I32, _I, _V, _I64, _V]),
     "stag_edge_softmax": (_I, [_GP, _V, _I32, _V, _V]),
     "stag_edge_softmax_bwd": (_I, [_GP, _V, _V, _I32, _V, _V]),

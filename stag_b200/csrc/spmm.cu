@@ -1650,6 +1650,7 @@ __global__ void emit_wh_kernel(const AggParams p, float* __restrict__ w_out, flo
 }  // namespace stag
 #include "spmm_tc.cuh"
 #include "spmm_wq.cuh"
+#include "noise_kl.cuh"
 namespace stag {
 
 // Philox blocks needed by `width` channels: 8 per whole 64-channel group, one per started quad of
@@ -2204,6 +2205,78 @@ extern "C" int stag_noise_emit(const StagNoise* noise, int64_t num_edges, int32_
     case STAG_NOISE_UNIFORM: emit_kernel<STAG_NOISE_UNIFORM><<<grid, 256, 0, stream>>>(p, w_out, eps_out); break;
     default: emit_kernel<STAG_NOISE_BERNOULLI><<<grid, 256, 0, stream>>>(p, w_out, eps_out); break;
   }
+  STAG_LAUNCH_CHECK();
+  return STAG_OK;
+}
+
+extern "C" size_t stag_noise_kl_workspace_bytes(int32_t K) {
+  if (K <= 0) return 0;
+  const size_t kpad = (size_t)((K + 63) / 64) * 64;
+  const size_t grid = (size_t)num_sms() * 4;
+  return align_up(grid * 4 * sizeof(double), 256) + align_up(grid * 2 * kpad * sizeof(float), 256);
+}
+
+extern "C" int stag_noise_kl(const StagNoise* noise, int64_t num_edges, int32_t S, const StagPrior* prior, double* sums,
+                             float* dparam0, float* dparam1, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  STAG_CHECK_ARG(noise != nullptr && prior != nullptr && sums != nullptr, "stag_noise_kl: null argument");
+  STAG_CHECK_ARG(noise->K > 0 && S > 0 && num_edges >= 0 && num_edges < (1ll << 31), "stag_noise_kl: bad sizes");
+  int rc = check_noise(noise, noise->K, num_edges, "stag_noise_kl");
+  if (rc) return rc;
+  if (noise->kind != STAG_NOISE_NORMAL && noise->kind != STAG_NOISE_UNIFORM) {
+    set_error("stag_noise_kl: the posterior must be a reparameterised Normal or Uniform drawn by the Box-Muller / uniform "
+              "generators (kind %d)", noise->kind);
+    return STAG_EUNSUPPORTED;
+  }
+  if (noise->in_norm) {
+    set_error("stag_noise_kl: in-norm rescales the sample by a per-row factor the edge pass does not have");
+    return STAG_EUNSUPPORTED;
+  }
+  STAG_CHECK_ARG(prior->kind == STAG_PRIOR_NORMAL_MIXTURE && prior->M >= 1 && prior->M <= STAG_PRIOR_MAX_COMPONENTS,
+                 "stag_noise_kl: prior must be a mixture of 1..%d Normals", STAG_PRIOR_MAX_COMPONENTS);
+  STAG_CHECK_ARG((dparam0 == nullptr) == (dparam1 == nullptr), "stag_noise_kl: pass both gradient outputs or neither");
+  const size_t need = stag_noise_kl_workspace_bytes(noise->K);
+  if (!ws || ws_bytes < need) {
+    set_error("stag_noise_kl: workspace %zu < required %zu", ws_bytes, need);
+    return STAG_EWORKSPACE;
+  }
+  KlParams p = {};
+  p.E = num_edges; p.S = S; p.K = noise->K;
+  p.nblk = blocks_for(noise->K);
+  p.kpad = (noise->K + 63) / 64 * 64;
+  p.pshape = noise->param_shape; p.relu = noise->relu; p.sample_base = noise->sample_base;
+  p.p0 = noise->p0; p.p1 = noise->p1;
+  p.key = make_key(noise->seed, noise->offset);
+  p.M = prior->M;
+  double wsum = 0.0;
+  for (int m = 0; m < prior->M; ++m) {
+    STAG_CHECK_ARG(prior->weight[m] > 0.f && prior->scale[m] > 0.f, "stag_noise_kl: prior weights and scales must be positive");
+    wsum += prior->weight[m];
+  }
+  for (int m = 0; m < prior->M; ++m) {
+    p.c_m[m] = (float)(log((double)prior->weight[m] / wsum) - log((double)prior->scale[m]) - 0.9189385332046727);
+    p.mu_m[m] = prior->loc[m];
+    p.is_m[m] = 1.0f / prior->scale[m];
+  }
+  p.dp0 = dparam0; p.dp1 = dparam1;
+  const int grid = kl_grid(num_edges);
+  p.cta_sums = (double*)ws;
+  p.cta_ch = (float*)((char*)ws + align_up((size_t)num_sms() * 4 * 4 * sizeof(double), 256));
+  const bool grads = dparam0 != nullptr;
+  const size_t smem = (grads && p.pshape == STAG_PARAM_CHANNEL) ? (size_t)KL_WARPS * 2 * p.kpad * sizeof(float) : 0;
+  if (num_edges > 0) {
+#define STAG_KL_LAUNCH(KIND, G)                                                                                      \
+  do {                                                                                                               \
+    if (smem > 48 * 1024)                                                                                            \
+      STAG_CUDA(cudaFuncSetAttribute(noise_kl_kernel<KIND, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    noise_kl_kernel<KIND, G><<<grid, KL_THREADS, smem, stream>>>(p);                                                  \
+  } while (0)
+    if (noise->kind == STAG_NOISE_NORMAL) { if (grads) STAG_KL_LAUNCH(STAG_NOISE_NORMAL, true); else STAG_KL_LAUNCH(STAG_NOISE_NORMAL, false); }
+    else { if (grads) STAG_KL_LAUNCH(STAG_NOISE_UNIFORM, true); else STAG_KL_LAUNCH(STAG_NOISE_UNIFORM, false); }
+#undef STAG_KL_LAUNCH
+    STAG_LAUNCH_CHECK();
+  }
+  noise_kl_finalize<<<1, 256, 0, stream>>>(p, num_edges > 0 ? grid : 0, grads ? 1 : 0, sums);
   STAG_LAUNCH_CHECK();
   return STAG_OK;
 }

@@ -204,6 +204,15 @@ class StagLayer(torch.nn.Module):
             return torch.distributions.kl_divergence(
                 self.q_a.base_distribution, self.p_a.base_distribution).mean()
         except Exception:
+            # no analytic KL (a mixture prior): the reference evaluates both log-probs on the stored [E,K] sample
+            # (stag/layers.py:141-143).  When the forward was fused that sample was never stored: stag_noise_kl
+            # regenerates it from the forward's (seed, offset) and reduces the two sums on the fly.
+            spec = self._noise_spec
+            if spec is not None and self._noise_tensor is None and spec.kind in ("normal", "uniform") \
+                    and not spec.in_norm and spec.p0.is_cuda and spec.lib_kind != ops._lib.NOISE_NORMAL_HADAMARD:
+                prior = ops.describe_prior(self.p_a)
+                if prior is not None:
+                    return ops.fused_kl_fallback(spec, prior)
             w = self._edge_weight_sample
             return self.q_a.log_prob(w).sum(dim=-1).mean() - self.p_a.log_prob(w).sum(dim=-1).mean()
 

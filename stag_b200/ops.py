@@ -531,6 +531,84 @@ class _FusedNLL(torch.autograd.Function):
         return dpr * (g.to(torch.float32) / count).reshape(-1, 1, 1), None, None, None
 
 
+def describe_prior(p_a):
+    """(weights, locs, scales) python lists when `p_a` is a Normal with one scalar parameter pair or a
+    MixtureSameFamily(Categorical, Normal) over up to 8 scalar components without trainable parameters -- the priors
+    ``stag_noise_kl`` evaluates in the kernel -- else None."""
+    d = getattr(p_a, "base_distribution", p_a)
+    td = torch.distributions
+    try:
+        if isinstance(d, td.MixtureSameFamily):
+            comp, mix = d.component_distribution, d.mixture_distribution
+            if not isinstance(comp, td.Normal) or comp.loc.dim() != 1 or comp.loc.numel() > _lib.PRIOR_MAX_COMPONENTS:
+                return None
+            ts = (mix.probs, comp.loc, comp.scale)
+        elif isinstance(d, td.Normal) and d.loc.numel() == 1 and d.scale.numel() == 1:
+            ts = (torch.ones(1), d.loc.reshape(1), d.scale.reshape(1))
+        else:
+            return None
+        if any(t.requires_grad for t in ts):
+            return None
+        return tuple([float(v) for v in t.detach().cpu().reshape(-1)] for t in ts)
+    except Exception:
+        return None
+
+
+class _NoiseKL(torch.autograd.Function):
+    """(sum log q(w), sum log p(w)) over the regenerated sample of a NoiseSpec (stag_noise_kl): no [E,K] tensor."""
+
+    @staticmethod
+    def forward(ctx, spec, prior, p0, p1):
+        dev = p0.device
+        _require_cuda(p0, "noise parameter")
+        lib = _lib.load()
+        E, K, S = spec.num_edges, spec.K, spec.n_samples
+        p0c, p1c = _c(p0), _c(p1)
+        pr = _lib.StagPrior()
+        pr.kind, pr.M = _lib.PRIOR_NORMAL_MIXTURE, len(prior[0])
+        for m in range(pr.M):
+            pr.weight[m], pr.loc[m], pr.scale[m] = prior[0][m], prior[1][m], prior[2][m]
+        need = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        n = {_lib.PARAM_SCALAR: 1, _lib.PARAM_CHANNEL: K, _lib.PARAM_EDGE: E, _lib.PARAM_EDGE_CHANNEL: E * K}[spec.param_shape]
+        d0 = torch.zeros(n, dtype=torch.float32, device=dev) if need else None
+        d1 = torch.zeros(n, dtype=torch.float32, device=dev) if need else None
+        sums = torch.empty(2, dtype=torch.float64, device=dev)
+        ws = torch.empty(max(lib.stag_noise_kl_workspace_bytes(K), 256), dtype=torch.uint8, device=dev)
+        nz = _fill_noise(spec, spec.lib_kind, K, p0c, p1c, None, spec.relu, False, spec.sample_base,
+                         spec.seed, spec.offset, spec.param_shape)
+        with _on_device(dev):
+            _lib.check(lib.stag_noise_kl(ctypes.byref(nz), E, S, ctypes.byref(pr), sums.data_ptr(), _ptr(d0), _ptr(d1),
+                                         ws.data_ptr(), ws.numel(), _stream(dev)))
+        ctx.save_for_backward(d0, d1)
+        ctx.shapes = (p0.shape, p1.shape)
+        return sums.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gsums):
+        d0, d1 = ctx.saved_tensors
+        g0 = g1 = None
+        if d0 is not None:
+            # d(sum log q - sum log p) came out of the kernel as one tensor: the layer only ever differentiates
+            # c * (sums[0] - sums[1]), so gsums = (c, -c)
+            c = gsums[0]
+            s0, s1 = ctx.shapes
+            if ctx.needs_input_grad[2]:
+                g0 = (c * d0).reshape(s0) if d0.numel() == max(1, _numel(s0)) else (c * d0).sum_to_size(s0)
+            if ctx.needs_input_grad[3]:
+                g1 = (c * d1).reshape(s1) if d1.numel() == max(1, _numel(s1)) else (c * d1).sum_to_size(s1)
+        return None, None, g0, g1
+
+
+def fused_kl_fallback(spec, prior):
+    """``q.log_prob(w).sum(-1).mean() - p.log_prob(w).sum(-1).mean()`` of the reference's KL fallback
+    (stag/layers.py:139-141) over the sample(s) `spec` describes, evaluated by ``stag_noise_kl`` from the regenerated
+    variates: no ``[E,K]`` allocation.  `prior` = ``describe_prior(p_a)``.  Differentiable w.r.t. the parameters of q."""
+    if spec.kind not in ("normal", "uniform") or spec.in_norm or spec.lib_kind == _lib.NOISE_NORMAL_HADAMARD:
+        raise ValueError("fused KL fallback: reparameterised Normal / Uniform posteriors without in-norm only")
+    sums = _NoiseKL.apply(spec, prior, spec.p0, spec.p1)
+    return (sums[0] - sums[1]) / float(max(spec.n_samples, 1) * max(spec.num_edges, 1))
+
+
 def fused_nll(probs, y, mask=None, kind="categorical"):
     """``[S]`` masked mean NLLs of ``probs [S,N,C]`` (or ``[N,C]`` -> scalar) under Categorical(probs=.) with labels
     ``y [N]`` or Bernoulli(probs=.) with labels ``y [N,C]``: one kernel pass for all samples, forward and gradient."""
