@@ -90,10 +90,19 @@ def _to_channels(slots, K):
     return out[:, :K]
 
 
+def _edge_ids(num_edges):
+    """`num_edges` is either a count (edges 0 .. E-1, original order) or an array of edge ids (the variates of
+    exactly those edges: row subsets of graphs too large to materialise [E,K] for)."""
+    if np.ndim(num_edges) == 0:
+        return np.arange(int(num_edges), dtype=np.uint32)
+    return np.asarray(num_edges).astype(np.uint32).reshape(-1)
+
+
 def halves(num_edges, K, sample, seed, offset):
     """uint32 [E, nblk, 8] -- the 16-bit integer h of every slot of every block (ORIGINAL edge order)."""
     nblk = n_blocks(K)
-    eid = np.arange(num_edges, dtype=np.uint32)[:, None]
+    eid = _edge_ids(num_edges)[:, None]
+    num_edges = eid.shape[0]
     q = np.arange(nblk, dtype=np.uint32)[None, :]
     r = np.stack(raw_block(eid, q, np.uint32(sample), seed, offset), axis=-1)      # [E, nblk, 4]
     h = np.stack([r & np.uint32(0xFFFF), r >> np.uint32(16)], axis=-1)               # [E, nblk, 4, 2]
@@ -112,7 +121,9 @@ M2LN2 = np.float64(np.float32(-2.0 * np.log(2.0)))
 
 def std_normal(num_edges, K, sample, seed, offset):
     nblk = n_blocks(K)
-    h = halves(num_edges, K, sample, seed, offset).reshape(num_edges, nblk * 4, 2).astype(np.float64)
+    h = halves(num_edges, K, sample, seed, offset)
+    num_edges = h.shape[0]
+    h = h.reshape(num_edges, nblk * 4, 2).astype(np.float64)
     u1 = (h[..., 0] + 0.5) * 2.0 ** -16
     rad = np.sqrt(M2LN2 * np.log2(u1))
     ang = np.float32((8388608.0 + h[..., 1]) * K_ANG + C_ANG).astype(np.float64)   # exact fp32 fma

@@ -130,6 +130,20 @@ def test_c4_molhiv_shaped_batch_vi_readout():
         return h.detach().clone(), {k: p.grad.clone() for k, p in layers.named_parameters()}
     h1, g1 = run(True)
     h2, g2 = run(False)
+    # ... and against the ORACLE at this shape: the first layer's aggregation with the noise of the numpy
+    # restatement of the generator (not the emitted tensor), summed by the torch restatement of update_all
+    from oracle import ref_philox, ref_spmm
+    src_b, dst_b = bg.edges()
+    loc = layers[0].q_a.loc.detach()
+    scale = layers[0].q_a.log_scale.detach().exp()
+    spec0 = stag.ops.NoiseSpec("normal", loc, scale, 9, bg.number_of_edges(), seed=5, offset=2)
+    ss, ds = bg._s.scale(False, "rsqrt"), bg._s.scale(True, "rsqrt")
+    got = stag.ops.stochastic_aggregate(bg, x, spec0, src_scale=ss, dst_scale=ds)
+    w = ref_philox.noise("normal", bg.number_of_edges(), 9, 0, 5, 2, loc.cpu().numpy(), scale.cpu().numpy())
+    exp = ref_spmm.aggregate(src_b.cpu(), dst_b.cpu(), N, x.cpu().double(), T(w).double(),
+                             src_scale=ss.cpu().double(), dst_scale=ds.cpu().double())
+    assert float((got.cpu().double() - exp).abs().max()) <= 1e-5 * float(exp.abs().max())
+    assert bool(((got.cpu().double() - exp).abs() <= 1e-5 * exp.abs() + 1e-6 * exp.abs().max()).all())
     assert h1.shape == (32, 16)
     assert rel(h1, h2) < 1e-5
     for k in g1:
@@ -167,11 +181,48 @@ def test_c5_products_shaped_properties():
     out.backward(y)
     rhs = (x.detach().double() * x.grad.double()).sum()
     assert abs(float(lhs - rhs)) <= 1e-6 * float(out.detach().double().abs().mul(y.double().abs()).sum())
-    part = P.RowPartition(T(src), T(dst), N, 3, 8)           # rank 3 of 8
+    # ---- the fused kernels against the ORACLE at this shape: 3 000 random rows, their in-edges from the
+    # CSC, the noise of exactly those edges from the numpy restatement of the generator (oracle/ref_philox.py), the
+    # reference's sum in edge-id order in float64 (stag/zoo/gcn.py:63,94-96 with fn.mean)
+    from oracle import ref_philox
+    full = sb.ops.stochastic_aggregate(g, x.detach(), spec(E), reduce="mean", n_samples=1)[0]
+    rows = torch.from_numpy(np.random.default_rng(1).choice(N, 3000, replace=False)).cuda()
+
+    def oracle_rows(indptr, indices, eid, rows, operand, row_scale):
+        a, b = indptr[rows].long(), indptr[rows + 1].long()
+        cnt = (b - a).cpu().numpy()
+        pos = torch.cat([torch.arange(int(lo_), int(hi_), device="cuda") for lo_, hi_ in zip(a.tolist(), b.tolist())])
+        ids, nbr = eid.long()[pos].cpu().numpy(), indices.long()[pos]
+        w = ref_philox.noise("normal", ids, D, 0, 3, 9, 1.0, 0.4).astype(np.float64)
+        msg = w * operand[nbr].double().cpu().numpy()
+        seg = np.repeat(np.arange(len(cnt)), cnt)
+        exp = np.zeros((len(cnt), D))
+        np.add.at(exp, seg, msg)                       # stored-edge order = edge-id order within a row
+        return exp * row_scale[:, None]
+    inv_in = 1.0 / np.maximum((indptr[rows + 1] - indptr[rows]).cpu().numpy(), 1)
+    exp = oracle_rows(indptr, indices, eid, rows, x.detach(), inv_in)
+    got = full[rows].double().cpu().numpy()
+    assert np.all(np.abs(got - exp) <= 1e-5 * np.abs(exp) + 1e-6 * np.abs(exp).max())
+    # transposed pass: dX[u] = sum over out-edges of w * (dOut[v] / clamp(indeg(v), 1)), 3 000 random source rows
+    ptr_r, idx_r, eid_r = g.adj_tensors("csr")
+    dscale = 1.0 / torch.clamp((indptr[1:] - indptr[:-1]).float(), min=1)
+    expd = oracle_rows(ptr_r, idx_r, eid_r, rows, y[0] * dscale[:, None], np.ones(len(rows)))
+    gotd = x.grad[rows].double().cpu().numpy()
+    assert np.all(np.abs(gotd - expd) <= 1e-5 * np.abs(expd) + 1e-6 * np.abs(expd).max())
+    del full
+    # ---- 1-D row partition, rank 3 of 8: whole-block form and halo form reproduce the unpartitioned rows bitwise ----
+    ref = sb.ops.stochastic_aggregate(g, x.detach(), spec(E), n_samples=1)[0]
+    part = P.RowPartition(T(src), T(dst), N, 3, 8, halo=False)
     lg = part.local_graph(sb.Graph).to("cuda")
     lo = sb.ops.stochastic_aggregate(lg, x.detach(), spec(lg.number_of_edges()), n_samples=1)[0]
-    full = sb.ops.stochastic_aggregate(g, x.detach(), spec(E), n_samples=1)[0]
-    assert torch.equal(lo[part.lo:part.hi], full[part.lo:part.hi])
+    assert torch.equal(lo[part.lo:part.hi], ref[part.lo:part.hi])
+    del lo, lg
+    hp = P.RowPartition(T(src).cuda(), T(dst).cuda(), N, 3, 8)     # halo plan; the exchange itself is emulated by indexing
+    hg = hp.local_graph(sb.Graph)
+    assert hg.number_of_nodes() == hp.n_own and hg.number_of_src_nodes() == hp.n_ext
+    x_ext = torch.cat([x.detach()[hp.lo:hp.hi], x.detach()[hp.need]])
+    lo = sb.ops.stochastic_aggregate(hg, x_ext, spec(hg.number_of_edges()), n_samples=1)[0]
+    assert lo.shape == (hp.n_own, D) and torch.equal(lo, ref[hp.lo:hp.hi])
 
 
 def test_c2_arxiv_shaped_training_step():

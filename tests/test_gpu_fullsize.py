@@ -97,8 +97,13 @@ def test_row_partition_keeps_global_noise(arxiv):
     full = sb.ops.stochastic_aggregate(g, x, sp(E), n_samples=1)[0]
     ts, td = torch.from_numpy(src), torch.from_numpy(dst)
     for rank in range(2):
-        part = P.RowPartition(ts, td, N, rank, 2)
+        part = P.RowPartition(ts, td, N, rank, 2, halo=False)      # whole-block form: local graph over all N nodes
         lg = part.local_graph(sb.Graph).to("cuda")
         out = sb.ops.stochastic_aggregate(lg, x, sp(lg.number_of_edges()), n_samples=1)[0]
         assert torch.equal(out[part.lo:part.hi], full[part.lo:part.hi])
         assert float(out[: part.lo].abs().sum()) == 0.0 and float(out[part.hi:].abs().sum()) == 0.0
+        hp = P.RowPartition(ts.cuda(), td.cuda(), N, rank, 2)      # halo form: bipartite local graph, referenced rows only
+        hg = hp.local_graph(sb.Graph)
+        x_ext = torch.cat([x[hp.lo:hp.hi], x[hp.need]])            # what the exchange delivers
+        out = sb.ops.stochastic_aggregate(hg, x_ext, sp(hg.number_of_edges()), n_samples=1)[0]
+        assert out.shape[0] == hp.n_own and torch.equal(out, full[hp.lo:hp.hi])

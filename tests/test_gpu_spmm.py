@@ -19,6 +19,13 @@ def close(a, b, rtol=RTOL, what=""):
     scale = max(np.abs(b).max(), 1e-30) if b.size else 1.0
     err = np.abs(a - b).max() / scale if b.size else 0.0
     assert err <= rtol, "%s: max err / max|ref| = %.3e > %.1e" % (what, err, rtol)
+    # ... and ELEMENTWISE: a small entry (zero-in-degree neighbourhoods, hub tails) may not be wrong by
+    # more than rtol of ITS OWN value plus the fp32 cancellation floor of a sum of terms of size `scale`
+    # (same form as tests/test_oracle_cpu.py)
+    if b.size:
+        bad = np.abs(a - b) > rtol * np.abs(b) + 1e-6 * scale
+        assert not bad.any(), "%s: %d entries beyond rtol %.1e elementwise (worst |a-b| = %.3e at |ref| = %.3e)" % (
+            what, int(bad.sum()), rtol, np.abs(a - b)[bad].max(), np.abs(b)[bad][np.abs(a - b)[bad].argmax()])
 
 
 def make_base(name, d):
