@@ -399,7 +399,7 @@ def run_ours(args, rank, world):
     peak, peak_src = peaks()
     achieved = alg / (avg_ms * 1e-3) / 1e9
     step_bytes = bytes_fwd(S, True) + 2 * bytes_fwd(S, False) + 2 * bytes_bwd(S, vi, False) + bytes_bwd(S, vi, True)
-    roof = {"bound": "hbm", "kernel": ("stag::agg_tc_kernel (%s launches)" if path.normal_kind == path._lib.NOISE_NORMAL_HADAMARD
+    roof = {"bound": "hbm", "kernel": ("stag::agg_wh_quad_kernel (tensor-core normal generator, %s launches)" if path.normal_kind == path._lib.NOISE_NORMAL_HADAMARD
                        else "stag::agg_stream_kernel<NORMAL, 2 blocks per lane> (%s launches)") % dom, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
@@ -460,9 +460,9 @@ def main():
     ap.add_argument("--mode", default="mle", choices=["mle", "vi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the multi_gpu legs (collectives inside the timed region)")
-    ap.add_argument("--normal", default="boxmuller", choices=["hadamard", "boxmuller"],
+    ap.add_argument("--normal", default="hadamard", choices=["hadamard", "boxmuller"],
                     help="standard-normal generator of the fused kernels: tensor-core Walsh-Hadamard mix "
-                         "(agg_tc_kernel) or 16-bit Box-Muller (agg_stream_kernel)")
+                         "(agg_wh_quad_kernel) or 16-bit Box-Muller (agg_stream_kernel)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -56,13 +56,19 @@ enum {
 enum {
   STAG_NOISE_NONE = 0,      /* w == 1: plain copy_u/sum aggregation (edge_weight=None, stag/zoo/gcn.py:59) */
   STAG_NOISE_EXTERNAL = 1,  /* w read from a caller tensor [S,E,K] in ORIGINAL edge order (parity seam) */
-  STAG_NOISE_NORMAL = 2,    /* w = loc + scale*eps            torch/distributions/normal.py:82-85   */
+  /* w = loc + scale*eps (torch/distributions/normal.py:82-85).  eps: Box-Muller on the two 16-bit halves of a Philox
+   * word, u1 = (h_lo + 1/2) / 65536, u2 = (h_hi + 1/2) / 65536: 65 536 radii x 65 536 angles.  KNOWN LIMIT of this
+   * generator: the largest radius is sqrt(2 ln 2^17) = 4.854, so |eps| <= 4.854 -- a true normal puts 1.2e-6 of its
+   * mass beyond that (123 of 1e8 draws) and this generator none; within +-4.6 sigma it passes chi-square and KS tests
+   * at 1e8 draws (tests/test_gpu_rng_law.py).  STAG_NOISE_NORMAL_HADAMARD has no such cut. */
+  STAG_NOISE_NORMAL = 2,
   STAG_NOISE_UNIFORM = 3,   /* w = low + u*(high-low)         torch/distributions/uniform.py:85-88  */
   STAG_NOISE_BERNOULLI = 4, /* w = (u < probs)                torch/distributions/bernoulli.py:116-119 */
   /* w = loc + scale*eps like STAG_NOISE_NORMAL, with eps drawn by the tensor-core generator: the 128 channels of
-   * a group are the Walsh-Hadamard mix of 128 masked random FP8 bytes (csrc/spmm_tc.cuh; normal to 5.6e-6 in
-   * Kolmogorov distance).  A different stream than STAG_NOISE_NORMAL.  Fused path: K == D, D % 128 == 0, scalar
-   * or per-edge parameters, no relu / in_norm / parameter gradients; stag_noise_emit: K % 128 == 0. */
+   * a group are the Walsh-Hadamard mix of 128 masked random FP8 bytes (csrc/spmm_tc.cuh, spmm_wq.cuh; normal to
+   * 5.6e-6 in Kolmogorov distance, support to +-24 sigma, tails at the normal rate in tests/test_gpu_rng_law.py).
+   * A different stream than STAG_NOISE_NORMAL.  Fused path: K == D, D % 128 == 0, 32-byte aligned rows, scalar or
+   * per-edge parameters, no relu / in_norm / parameter gradients; stag_noise_emit: K % 128 == 0. */
   STAG_NOISE_NORMAL_HADAMARD = 5
 };
 

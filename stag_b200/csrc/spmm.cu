@@ -54,9 +54,6 @@ struct AggParams {
   const int32_t* erow;       // row of every stored edge
   const int32_t* eidf;       // edge id of every stored edge, bit 31 set on the last edge of its row
   const int4* rec;           // per-call edge records (edge_record_kernel), workspace
-  const int32_t* ebnd;       // tensor-core path: edge boundaries of the units (tc_bounds_kernel), workspace
-  const uint32_t* rowoff;    // tensor-core path: byte offset of the output row of every stored edge, workspace
-  int nunits;
   int num_items;
   uint32_t rk[2 * kPhiloxRounds];  // Philox round keys
   uint32_t kf;                     // 0x4B000000 (2^23 as float bits), read from the constant bank by PRMT
@@ -1668,7 +1665,7 @@ static int lpr_log2_for(int nblk) {
 }
 
 struct WsLayout {
-  size_t part_acc, part_w, dp_partial, rec, ebnd, rowoff, total;
+  size_t part_acc, part_w, dp_partial, rec, total;
 };
 
 static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
@@ -1683,10 +1680,6 @@ static WsLayout ws_layout(const StagGraph* g, int D, int S, int grid_max) {
   off += align_up((size_t)grid_max * 2 * D8 * 4 + 16, 256);
   L.rec = off;
   off += align_up((size_t)g->num_edges * 16 + 16, 256);
-  L.ebnd = off;
-  off += align_up((size_t)(g->num_edges / TC_UNIT_EDGES + 2) * 4, 256);
-  L.rowoff = off;
-  off += align_up((size_t)g->num_edges * 4 + 16, 256);
   L.total = off;
   return L;
 }
@@ -1980,29 +1973,23 @@ extern "C" int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, in
     vec = vec && aligned16(noise->p0) && (noise->p1 == nullptr || aligned16(noise->p1));
   if (norm_scale_out && noise->K != 1) vec = vec && aligned16(norm_scale_out);
   if (noise->kind == STAG_NOISE_NORMAL_HADAMARD) {
-    // tensor-core noise path (spmm_tc.cuh): hubs need no partial sums, a thread owns a channel of the whole row
+    // tensor-core noise path (spmm_wq.cuh)
     if (g->num_edges == 0) {
       p.kind = STAG_NOISE_NONE;  // nothing to draw: the streaming kernel's tail clears the rows
     } else {
-      const bool ok = noise->K == D && D % 128 == 0 && vec && !noise->relu && !noise->in_norm &&
+      // 256-bit gathers and row stores: 32-byte aligned rows
+      const bool a32 = (((uintptr_t)x | (uintptr_t)out) & 31) == 0 && ldx % 8 == 0 && ldo % 8 == 0 &&
+                       x_sample_stride % 8 == 0 && out_sample_stride % 8 == 0;
+      const bool ok = noise->K == D && D % 128 == 0 && vec && a32 && !noise->relu && !noise->in_norm &&
                       (noise->param_shape == STAG_PARAM_SCALAR || noise->param_shape == STAG_PARAM_EDGE) &&
-                      g->erow && g->eidf && g->num_cols * ldx * 4 < (1ll << 32) && g->num_rows * ldo * 4 < (1ll << 32);
+                      g->erow && g->eidf && g->items && g->num_cols * ldx * 4 < (1ll << 32) && g->num_rows * ldo * 4 < (1ll << 32);
       if (!ok) {
-        set_error("stag_spmm_fwd: STAG_NOISE_NORMAL_HADAMARD needs K == D, D %% 128 == 0, 16-byte aligned rows, scalar "
-                  "or per-edge parameters, no relu / in_norm, a graph built with erow / eidf and a gathered operand "
+        set_error("stag_spmm_fwd: STAG_NOISE_NORMAL_HADAMARD needs K == D, D %% 128 == 0, 32-byte aligned rows, scalar "
+                  "or per-edge parameters, no relu / in_norm, a graph built with items / erow / eidf and a gathered operand "
                   "below 4 GB (K=%d D=%d)", noise->K, D);
         return STAG_EUNSUPPORTED;
       }
-      p.ebnd = (const int32_t*)((char*)ws + L.ebnd);
-      p.rowoff = (const uint32_t*)((char*)ws + L.rowoff);
-      // two forms of the kernel (spmm_tc.cuh): 2 = tensor cores feeding the 16-channels-per-lane stream (default, needs
-      // the stream items), 1 = channel per thread
-      static const char* form = getenv("STAG_TC_FORM");
-      if ((form && atoi(form) == 1) || !g->items) return launch_tc(p, stream);
-      // 3 (default) = four lanes per stream reading z in their own layout, 256-bit gathers: 32-byte aligned rows
-      const bool a32 = (((uintptr_t)x | (uintptr_t)out) & 31) == 0 && ldx % 8 == 0 && ldo % 8 == 0 &&
-                       x_sample_stride % 8 == 0 && out_sample_stride % 8 == 0;
-      rc = ((form && atoi(form) == 2) || !a32) ? launch_wh_stream(p, stream) : launch_wh_quad(p, stream);
+      rc = launch_wh_quad(p, stream);
       if (rc) return rc;
       if (g->num_hubs > 0) {
         const int64_t total = (int64_t)S * g->num_hubs * D;

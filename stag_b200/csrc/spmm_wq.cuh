@@ -52,6 +52,22 @@ __device__ __forceinline__ void tc_ldtm_wait32(uint32_t (&v)[32]) {
                :
                : "memory");
 }
+__device__ __forceinline__ void tc_ldtm_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ldtm_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void ldg256(const char* src, float4& a, float4& b) {
   asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
@@ -373,14 +389,15 @@ static int launch_wh_quad(const AggParams& p, cudaStream_t stream) {
     edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(p, const_cast<int4*>(p.rec), 3);
     STAG_LAUNCH_CHECK();
   }
-  static const char* var = getenv("STAG_WQ_VARIANT");  // tuning knob
+  // XB = 4 (a whole round of gathered rows in flight per lane) with two TMEM accumulators is the fastest measured
+  // form (profiles/r02_wq_forms.txt); STAG_WQ_VARIANT selects the others for A/B runs
+  static const char* var = getenv("STAG_WQ_VARIANT");
   const int v = var ? atoi(var) : 0;
   switch (v) {
-    case 1: return launch_wh_quad_inst<4, 4, true, 2>(p, stream);
-    case 2: return launch_wh_quad_inst<8, 2, false, 2>(p, stream);
+    case 1: return launch_wh_quad_inst<4, 4, false, 2>(p, stream);
+    case 2: return launch_wh_quad_inst<4, 2, false, 3>(p, stream);
     case 3: return launch_wh_quad_inst<8, 2, true, 2>(p, stream);
-    case 4: return launch_wh_quad_inst<8, 1, false, 2>(p, stream);
-    default: return launch_wh_quad_inst<4, 4, false, 2>(p, stream);
+    default: return launch_wh_quad_inst<4, 4, true, 2>(p, stream);
   }
 }
 

@@ -20,8 +20,9 @@ import torch
 from . import _lib, random as _random
 from .graph import as_graph
 
-# 'auto' = the tensor-core generator wherever the fused kernel takes it, else Box-Muller
-_DEFAULT_NORMAL_GENERATOR = "boxmuller"
+# 'auto' = the tensor-core generator wherever the fused kernel takes it (K % 128 == 0, scalar / per-edge parameters
+# without gradients, no relu / in-norm: 1.49 ms per arxiv launch against 1.68), else Box-Muller
+_DEFAULT_NORMAL_GENERATOR = "auto"
 _KIND = {"normal": _lib.NOISE_NORMAL, "uniform": _lib.NOISE_UNIFORM, "bernoulli": _lib.NOISE_BERNOULLI}
 
 
@@ -53,9 +54,9 @@ class NoiseSpec:
     sample_base      global index of the first Monte-Carlo sample of this call
     generator        how standard normals are drawn: 'boxmuller' (16-bit Box-Muller in the CUDA cores),
                      'hadamard' (Walsh-Hadamard mix of random FP8 bytes on the tensor cores,
-                     csrc/spmm_tc.cuh) or None = hadamard wherever the fused kernel takes it (K a
-                     multiple of 128, scalar or per-edge parameters without gradients, no relu / in-norm;
-                     env STAG_NORMAL_GENERATOR overrides).  The forward, the transposed pass and
+                     csrc/spmm_tc.cuh, spmm_wq.cuh) or None = hadamard wherever the fused kernel takes it (K a
+                     multiple of 128, scalar or per-edge parameters without gradients, no relu / in-norm),
+                     else boxmuller; env STAG_NORMAL_GENERATOR (boxmuller | hadamard | auto) overrides the None case.  The forward, the transposed pass and
                      ``materialize`` of one spec always use the same generator.
     """
 

@@ -1,4 +1,4 @@
-"""GPU: the tensor-core normal generator (STAG_NOISE_NORMAL_HADAMARD, csrc/spmm_tc.cuh).
+"""GPU: the tensor-core normal generator (STAG_NOISE_NORMAL_HADAMARD, csrc/spmm_tc.cuh + spmm_wq.cuh).
 (1) the emitted stream equals the numpy restatement BIT FOR BIT (every sum is exact in fp32);
 (2) the tensor-core sums the fused kernel consumes equal the emitted stream bit for bit;
 (3) the law: moments, Kolmogorov-Smirnov, independence across channel / edge / sample / offset;
@@ -75,19 +75,6 @@ def test_moments_ks_independence():
     assert np.abs(C - np.eye(K)).max() < 6 / np.sqrt(E)
     C2 = np.corrcoef((z ** 2).T)
     assert np.abs(C2 - np.eye(K)).max() < 6 / np.sqrt(E)
-
-
-def test_channel_per_thread_form_in_a_fresh_process():
-    """agg_tc_kernel (STAG_TC_FORM=1) against the same oracle: the fused parity cases of this file, rerun."""
-    import os
-    import subprocess
-    import sys
-    if os.environ.get("STAG_TC_FORM") == "1":
-        pytest.skip("already running the channel-per-thread form")
-    env = dict(os.environ, STAG_TC_FORM="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-x", "-q", "-k",
-                        "fused_forward or bitwise or per_edge"], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("N,E,D,S,shared,hub", [

@@ -48,7 +48,7 @@ def test_fused_kl_equals_the_reference_expression_on_the_emitted_sample(kind, sh
     a0 = p0.detach().double().requires_grad_(True)
     a1 = p1.detach().double().requires_grad_(True)
     eps_spec = ops.NoiseSpec(kind, torch.zeros((), device=dev), torch.ones((), device=dev), K, E, seed=17, offset=3,
-                             sample_base=2, n_samples=S, batched=True)
+                             sample_base=2, n_samples=S, batched=True, generator="boxmuller")
     raw = eps_spec.materialize(n_samples=S).double()      # Normal(0,1): eps; Uniform(0,1): u
     if kind == "normal":
         w = a0 + a1 * raw

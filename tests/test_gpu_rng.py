@@ -231,7 +231,8 @@ def test_per_edge_parameter_gradients_for_batched_samples(kind, pshape, D, K, re
     launches = sb._lib.load().stag_launch_count() - n0
     assert launches <= 12, launches          # not one backward launch per sample
     # oracle: per sample, autograd through the reparameterisation on the emitted raw variates
-    plain = sb.ops.NoiseSpec(kind, pa.detach(), pb.detach(), K, e, seed=5, offset=6, n_samples=S)
+    plain = sb.ops.NoiseSpec(kind, pa.detach(), pb.detach(), K, e, seed=5, offset=6, n_samples=S,
+                             generator="boxmuller")   # the stream of the gradient kernels (parameters with gradients)
     lib = sb._lib.load()
     import ctypes
     raw = torch.empty((S, e, K), device="cuda")

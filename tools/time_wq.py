@@ -1,5 +1,6 @@
-"""Device time per launch of the headline aggregation with the tensor-core normal generator, per kernel variant
-(STAG_TC_FORM / STAG_WQ_VARIANT are read once per process: one process per variant).  Usage: time_wq.py [shared]"""
+"""Device time per launch of the headline aggregation with the tensor-core normal generator (agg_wh_quad_kernel), per
+kernel variant (STAG_WQ_VARIANT is read once per process: one process per variant), next to the Box-Muller kernel.
+Usage: time_wq.py [shared | csr]"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -45,8 +46,7 @@ def t(fn, n=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 
-tag = "form=%s variant=%s %s" % (os.environ.get("STAG_TC_FORM", "3"), os.environ.get("STAG_WQ_VARIANT", "0"),
-                                 sys.argv[1] if len(sys.argv) > 1 else "per-sample")
+tag = "variant=%s %s" % (os.environ.get("STAG_WQ_VARIANT", "0"), sys.argv[1] if len(sys.argv) > 1 else "per-sample")
 th = t(lambda: fwd(noise(_lib.NOISE_NORMAL_HADAMARD)))
 ch = float(out.double().abs().sum())
 tb = t(lambda: fwd(noise(_lib.NOISE_NORMAL)))
