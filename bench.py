@@ -433,6 +433,15 @@ def run_ours(args, rank, world):
         path.act = path.gbuf = path.gout = path.dx0 = None   # the headline's buffers (7 GB) make room for the legs
         torch.cuda.empty_cache()
         multi = bench_multi.run_all(dev, dist, rank, world, args.steps, args.warmup, args.normal)
+    configs = unfused = None
+    if world == 1 and not args.no_configs:
+        # the other BASELINE.json configurations (C1, C3, C4, C5, vi mode) with the same timing method, and the
+        # reference's un-fused algorithm in plain torch ops on this GPU (a same-hardware baseline)
+        import bench_multi
+        path.act = path.gbuf = path.gout = path.dx0 = None
+        torch.cuda.empty_cache()
+        unfused = bench_multi.unfused_gpu_baseline(dev, src, dst, N_NODES, WIDTH, SIGMA)
+        configs = bench_multi.configs_single_gpu(dev, peak)
     if rank != 0:
         return
     cpu = cpu_baseline(args.mode) if (world == 1 and not args.no_cpu_baseline) else None
@@ -448,6 +457,9 @@ def run_ours(args, rank, world):
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if multi is not None:
         line["multi_gpu"] = multi
+    if configs is not None:
+        line["configs"] = configs
+        line["unfused_gpu_baseline"] = unfused
     print(json.dumps(line), flush=True)
 
 
@@ -459,6 +471,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="mle", choices=["mle", "vi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the `configs` dict (C1, C3, C4, C5, vi)")
     ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the multi_gpu legs (collectives inside the timed region)")
     ap.add_argument("--normal", default="hadamard", choices=["hadamard", "boxmuller"],
                     help="standard-normal generator of the fused kernels: tensor-core Walsh-Hadamard mix "

@@ -328,3 +328,132 @@ def run_all(dev, dist, rank, world, steps, warmup, normal):
         "boxmuller", bwd_chunk=8)
     out["seconds"] = time.perf_counter() - t0
     return out
+
+
+# ---- the other BASELINE.json configurations on one GPU (the `configs` dict of the N = 1 bench line) -----------------
+def _bytes_per_edge_sample(N, E, D, vi):
+    """algorithmic bytes of one layer, forward + transposed pass, per edge-sample."""
+    nd = 4.0 * N * D
+    fwd = 2 * nd + 4 * E + 4 * (N + 1) + 8 * N
+    bwd = (3 if vi else 2) * nd + 8 * E + 4 * (N + 1) + 8 * N
+    return (fwd + bwd) / E
+
+
+def config_row(dev, name, g, widths, S, vi, per_channel, iters, peak, warmup=3):
+    """One STEP = every aggregation of the configuration's layers, forward and backward, over S Monte-Carlo samples,
+    through the public operator (stag_b200.ops.stochastic_aggregate + autograd); CUDA events, features resident."""
+    from stag_b200.ops import NoiseSpec
+    g = g.to(dev)
+    N, E = g.number_of_nodes(), g.number_of_edges()
+    st = g._s
+    st.csx(True), st.csx(False)
+    ss, ds = st.scale(False, "rsqrt"), st.scale(True, "rsqrt")
+    gen = torch.Generator(device=dev).manual_seed(7)
+    layers = []
+    for li, D in enumerate(widths):
+        shape = (D,) if per_channel else ()
+        loc = torch.ones(shape, device=dev).requires_grad_(vi)
+        scale = torch.full(shape, 0.4, device=dev).requires_grad_(vi)
+        x = torch.randn((N, D) if li == 0 else (S, N, D), device=dev, generator=gen).requires_grad_(True)
+        gout = torch.randn(S, N, D, device=dev, generator=gen)
+        layers.append((D, loc, scale, x, gout))
+
+    def step():
+        for D, loc, scale, x, gout in layers:
+            spec = NoiseSpec("normal", loc, scale, D, E, n_samples=S, batched=True)
+            out = sb.ops.stochastic_aggregate(g, x, spec, src_scale=ss, dst_scale=ds, n_samples=S)
+            out.backward(gout)
+            x.grad = None
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    es = float(E) * S * len(widths)
+    nbytes = sum(_bytes_per_edge_sample(N, E, D, vi) for D in widths) * E * S
+    return {"workload": name, "N": N, "E": E, "widths": list(widths), "mc_samples": S, "mode": "vi" if vi else "mle",
+            "ms_per_step": ms, "value": es / ms / 1e6, "unit": "GEdge-samples/s",
+            "frac_of_hbm_roof": nbytes / ms / 1e6 / peak, "launches_per_step": 2 * len(widths)}
+
+
+def _batched_graphs(sizes, edges_per_node, seed):
+    rng = np.random.default_rng(seed)
+    gs = []
+    for n in sizes:
+        e = max(1, int(edges_per_node * n / 2))
+        s, d = rng.integers(0, n, e), rng.integers(0, n, e)
+        gs.append(sb.Graph(torch.from_numpy(np.concatenate([s, d])), torch.from_numpy(np.concatenate([d, s])), int(n)))
+    return sb.batch(gs)
+
+
+def configs_single_gpu(dev, peak):
+    """C1, C3, C4, C5 and the vi mode of C2 (SURVEY section 8 shapes), same timing method as the headline."""
+    import bench
+    rows = {}
+    rng = np.random.default_rng(0)
+    s, d = powerlaw_graph_device(2708, 10556, 0x57A6 + 1, 168, dev)
+    rows["c1_cora"] = config_row(dev, "C1 Cora-shaped (N 2 708, E 10 556), 3 layers 1433-16-16, S 4", sb.Graph(s, d, 2708),
+                                 [1433, 16, 16], 4, False, False, 50, peak)
+    s2, d2 = bench.synth_graph()
+    g2 = sb.Graph(torch.from_numpy(s2), torch.from_numpy(d2), bench.N_NODES)
+    rows["c2_arxiv_vi_rc"] = config_row(dev, "C2 arxiv-shaped, 3 layers, learned per-channel Normal noise (vi=True: d loc / d scale)",
+                                        g2, [128, 128, 128], 16, True, True, 5, peak)
+    del g2
+    torch.cuda.empty_cache()
+    sizes = rng.integers(1000, 3500, 2)
+    rows["c3_ppi_minibatch"] = config_row(dev, "C3 PPI-shaped minibatch (2 graphs), 3 layers 50-256-256, S 1 (training step)",
+                                          _batched_graphs(sizes, 28.7, 3), [50, 256, 256], 1, False, False, 50, peak)
+    sizes = rng.integers(1000, 3500, 24)
+    rows["c3_ppi_all_graphs"] = config_row(dev, "C3 PPI-shaped, all 24 graphs in one batch, S 4 (inference)",
+                                           _batched_graphs(sizes, 28.7, 3), [50, 256, 256], 4, False, False, 20, peak)
+    sizes = np.clip(rng.normal(25.5, 12, 32), 2, 80).astype(int)
+    rows["c4_molhiv_batch32"] = config_row(dev, "C4 molhiv-shaped batch of 32 molecules, 2 layers 9-16, per-channel learned Normal (vi), S 4",
+                                           _batched_graphs(sizes, 2.15, 4), [9, 16], 4, True, True, 50, peak)
+    sizes = np.clip(rng.normal(25.5, 12, 4096), 2, 80).astype(int)
+    rows["c4_molhiv_batch4096"] = config_row(dev, "C4 molhiv-shaped batch of 4 096 molecules, 2 layers 9-256, vi, S 4",
+                                             _batched_graphs(sizes, 2.15, 4), [9, 256], 4, True, True, 20, peak)
+    s5, d5 = powerlaw_graph_device(2449029, 61859140, 0x57A6 + 5, 17000, dev)
+    rows["c5_products_4_of_32_samples"] = config_row(dev, "C5 products-shaped (N 2 449 029, E 61 859 140, D 100), 1 layer, 4 of the 32 samples "
+                                                     "(one GPU's share at 8 GPUs)", sb.Graph(s5, d5, 2449029), [100], 4, False, False, 3, peak, warmup=2)
+    torch.cuda.empty_cache()
+    return rows
+
+
+def unfused_gpu_baseline(dev, src, dst, N, D, sigma=0.4, iters=5):
+    """the reference's algorithm on the SAME GPU, un-fused, in plain torch ops -- noise tensor [E,D]
+    materialised by torch.normal, message = x[src] * w, index_add into the destinations, autograd backward (what
+    stag/layers.py:115-129 + DGL's gspmm / gsddmm do, one layer x one MC sample per step).  This is NOT this library."""
+    src_t, dst_t = torch.as_tensor(src, device=dev), torch.as_tensor(dst, device=dev)
+    E = src_t.numel()
+    outdeg = torch.bincount(src_t, minlength=N).clamp_(min=1).float().pow_(-0.5)
+    indeg = torch.bincount(dst_t, minlength=N).clamp_(min=1).float().pow_(-0.5)
+    x = torch.randn(N, D, device=dev, requires_grad=True)
+    gout = torch.randn(N, D, device=dev)
+
+    def step():
+        w = 1.0 + sigma * torch.randn(E, D, device=dev)
+        msg = (x * outdeg[:, None])[src_t] * w
+        out = torch.zeros(N, D, device=dev).index_add_(0, dst_t, msg) * indeg[:, None]
+        out.backward(gout)
+        x.grad = None
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    return {"value": E / ms / 1e6, "unit": "GEdge-samples/s", "ms_per_layer_sample": ms,
+            "what": "the reference's algorithm un-fused in plain torch CUDA ops on this GPU (torch.randn [E,D] noise, gather, "
+                    "multiply, index_add, autograd backward), 1 layer x 1 MC sample per step; not DGL's kernels (DGL is not "
+                    "installable here) and not this library"}

@@ -1560,6 +1560,96 @@ __global__ void __launch_bounds__(256) edge_param_grads_kernel(const AggParams p
   }
 }
 
+// The common amortised case on the generator code of the hot kernel: Normal noise, [E,1] parameters (the `re`
+// posteriors of scripts/arxiv_rec: AmortizedDistribution(in_features, 1)), no relu, K == D made of whole 128-channel
+// groups, 128-bit rows.  8 lanes own one stored edge; a lane owns 16 channels of it (Philox blocks sl and sl + 8 of
+// every group: the quads at c, c + 32, c + 64, c + 96 of agg_stream_kernel<NB = 2>), round keys from the constant bank,
+// Box-Muller on packed FFMA2 / FMUL2:
+//     d loc[e] += sc sum_{s,c} x g        d scale[e] += sc sum_{s,c} x g eps
+// (eps = sqrt(2 ln 2) sqrt(-lg2 u1) cos / sin, the same variates as the forward).  4.8 ms -> see profiles/r02_modes.txt.
+__global__ void __launch_bounds__(256) edge_param_grads_fast_kernel(const AggParams p) {
+  const int lane = threadIdx.x & 31, sl = lane & 7;
+  const int64_t ngr = (int64_t)gridDim.x * (blockDim.x >> 3);
+  const int64_t g0 = (int64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const int64_t trips = (p.E + ngr - 1) / ngr;  // every group of a warp makes the same number of trips (shuffles below)
+  const int G = p.D >> 7;
+  const uint32_t kf = p.kf;
+  for (int64_t it = 0; it < trips; ++it) {
+    const int64_t j = g0 + it * ngr;
+    const bool on = j < p.E;
+    const int u = on ? __ldg(p.erow + j) : 0;
+    const int v = on ? __ldg(p.indices + j) : 0;
+    const uint32_t e = on ? (uint32_t)__ldg(p.eid + j) : 0u;
+    float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
+    if (on) {
+      for (int g = 0; g < G; ++g) {
+        const float* xrp = p.xrow + (int64_t)u * p.ldxr + 128 * g + 4 * sl;
+        const float* gvp = p.x + (int64_t)v * p.ldx + 128 * g + 4 * sl;
+        float4 xn[4], gn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          xn[q] = __ldg(reinterpret_cast<const float4*>(xrp + 32 * q));
+          gn[q] = __ldg(reinterpret_cast<const float4*>(gvp + 32 * q));
+        }
+        // samples innermost, the two rows of sample s + 1 requested before sample s is worked on (samples outermost,
+        // one [N,D] operand pair resident in L2 at a time, measured slower: 2.6 - 3.0 against 1.9 ms)
+        for (int s = 0; s < p.S; ++s) {
+          float2 d[8];  // x g of this lane's 16 channels, as pairs
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            d[2 * q] = __fmul2_rn(make_float2(xn[q].x, xn[q].y), make_float2(gn[q].x, gn[q].y));
+            d[2 * q + 1] = __fmul2_rn(make_float2(xn[q].z, xn[q].w), make_float2(gn[q].z, gn[q].w));
+          }
+          if (s + 1 < p.S) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              xn[q] = __ldg(reinterpret_cast<const float4*>(xrp + (int64_t)(s + 1) * p.xr_ss + 32 * q));
+              gn[q] = __ldg(reinterpret_cast<const float4*>(gvp + (int64_t)(s + 1) * p.x_ss + 32 * q));
+            }
+          }
+          const uint32_t smp = (uint32_t)(p.sample_base + s);
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            // block 16 g + sl + 8 b: channels 64 b + 4 sl + {0..3} (slots 0..3) and 64 b + 32 + 4 sl + {0..3} (slots 4..7)
+            const uint4 r4 = philox_rk((uint32_t)(16 * g + sl + 8 * b), e, smp, p.key.c3, p);
+            const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int ip = 0; ip < 2; ++ip) {
+              const uint32_t qa = w4[2 * ip], qb = w4[2 * ip + 1];
+              const float2 xl = make_float2(__uint_as_float(__byte_perm(qa, kf, 0x7610)), __uint_as_float(__byte_perm(qb, kf, 0x7610)));
+              const float2 xh = make_float2(__uint_as_float(__byte_perm(qa, kf, 0x7632)), __uint_as_float(__byte_perm(qb, kf, 0x7632)));
+              const float2 u1 = __ffma2_rn(xl, make_float2(1.52587890625e-05f, 1.52587890625e-05f),
+                                           make_float2(-127.99999237060547f, -127.99999237060547f));
+              const float2 ang = __ffma2_rn(xh, make_float2(9.58738019107841e-05f, 9.58738019107841e-05f),
+                                            make_float2(-804.2476806640625f, -804.2476806640625f));
+              const float ra = mufu_sqrt(-mufu_lg2(u1.x)), rb = mufu_sqrt(-mufu_lg2(u1.y));
+              // slots 4 ip + {0, 1} (word qa) and 4 ip + {2, 3} (word qb) of the block -> pairs d[4 b + 2 ip], d[4 b + 2 ip + 1]
+              const float2 za = __fmul2_rn(make_float2(mufu_cos(ang.x), mufu_sin(ang.x)), make_float2(ra, ra));
+              const float2 zb = __fmul2_rn(make_float2(mufu_cos(ang.y), mufu_sin(ang.y)), make_float2(rb, rb));
+              const float2 da = d[4 * b + 2 * ip], db = d[4 * b + 2 * ip + 1];
+              t0 = __fadd2_rn(t0, __fadd2_rn(da, db));
+              t1 = __ffma2_rn(da, za, t1);
+              t1 = __ffma2_rn(db, zb, t1);
+            }
+          }
+        }
+      }
+    }
+    float a0 = t0.x + t0.y, a1 = t1.x + t1.y;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (on && sl == 0) {
+      float sc = p.gscale ? __ldg(p.gscale + v) : 1.0f;
+      if (p.rscale) sc *= __ldg(p.rscale + u);
+      p.dp0[e] += sc * a0;
+      p.dp1[e] += sc * a1 * 1.1774100225154747f;  // sqrt(2 ln 2): the radius above is sqrt(-lg2 u1)
+    }
+  }
+}
+
 // noise materialisation (compat path + RNG tests): w[s,e,c]
 template <int KIND>
 __global__ void emit_kernel(const AggParams p, float* __restrict__ w_out, float* __restrict__ eps_out) {
@@ -2070,6 +2160,7 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
   if (dx) vec = vec && (lddx % 4 == 0) && (dx_sample_stride % 4 == 0) && aligned16(dx);
   if (noise->kind == STAG_NOISE_EXTERNAL && noise->K != 1)
     vec = vec && aligned16(noise->external) && (dw_external == nullptr || aligned16(dw_external));
+  const bool vec_rows = vec;  // feature / gradient rows take 128-bit accesses (the parameter tensors may still not)
   if (param_grads && noise->param_shape != STAG_PARAM_SCALAR && noise->K != 1)
     vec = vec && aligned16(noise->p0) && aligned16(noise->p1) && aligned16(dparam0) && aligned16(dparam1);
   if (edge_parallel) {
@@ -2079,7 +2170,10 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
       set_shape(q, D, S, g->num_cols, false, false);
       q.rec = (const int4*)((char*)ws + L.rec);
       q.xrow = nullptr; q.dp0 = q.dp1 = nullptr; q.dw_ext = nullptr;
-      rc = launch_agg<false>(q, vec, agg_grid(q), 0, stream);
+      // (the dX pass reads the parameters, never the gradient tensors: their alignment does not matter here)
+      const bool vec_dx = vec_rows && (noise->param_shape != STAG_PARAM_EDGE_CHANNEL ||
+                                       (aligned16(noise->p0) && aligned16(noise->p1)));
+      rc = launch_agg<false>(q, vec_dx, agg_grid(q), 0, stream);
       if (rc) return rc;
       if (g->num_hubs > 0) {
         const int64_t total = (int64_t)S * g->num_hubs * D;
@@ -2090,7 +2184,12 @@ extern "C" int stag_spmm_bwd(const StagGraph* g, const float* x, int64_t ldx, in
     if (p.E > 0) {
       const int64_t want = (p.E + 15) / 16;
       const int egrid = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
-      if (noise->kind == STAG_NOISE_NORMAL) {
+      const bool fast = noise->kind == STAG_NOISE_NORMAL && noise->param_shape == STAG_PARAM_EDGE && !noise->relu &&
+                        noise->K == D && D % 128 == 0 && vec_rows;   // [E,1] parameters: scalar reads / writes per edge
+      if (fast) {
+        const int64_t want8 = (p.E + 31) / 32;
+        edge_param_grads_fast_kernel<<<(int)(want8 < (int64_t)num_sms() * 16 ? want8 : (int64_t)num_sms() * 16), 256, 0, stream>>>(p);
+      } else if (noise->kind == STAG_NOISE_NORMAL) {
         if (vec) edge_param_grads_kernel<STAG_NOISE_NORMAL, true><<<egrid, 256, 0, stream>>>(p);
         else edge_param_grads_kernel<STAG_NOISE_NORMAL, false><<<egrid, 256, 0, stream>>>(p);
       } else {
