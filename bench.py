@@ -452,8 +452,9 @@ def run_ours(args, rank, world):
                        "normal_generator": ("hadamard (tensor cores)" if path.normal_kind == path._lib.NOISE_NORMAL_HADAMARD
                                             else "boxmuller (16-bit halves)"),
                        "sharded_unit": "MC samples (Philox sample index), no data-path collective",
-                       "l2": "per-launch inputs (1.39 GB activations per layer) exceed the 126 MB L2; "
-                             "layer-1 X (87 MB) is deliberately L2-resident across its 16 samples"},
+                       "l2": "per-launch inputs (1.39 GB activations per layer) exceed the 126 MB L2: nothing is L2-resident "
+                             "from one timed launch to the next (ncu: DRAM traffic 1.5x the algorithmic bytes on the per-sample "
+                             "launches, 1.7x on the layer-1 launch, whose shared X is re-fetched by most of the 16 samples)"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if multi is not None:
         line["multi_gpu"] = multi

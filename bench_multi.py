@@ -339,7 +339,7 @@ def _bytes_per_edge_sample(N, E, D, vi):
     return (fwd + bwd) / E
 
 
-def config_row(dev, name, g, widths, S, vi, per_channel, iters, peak, warmup=3):
+def config_row(dev, name, g, widths, S, vi, per_channel, iters, peak, warmup=3, graphed=False):
     """One STEP = every aggregation of the configuration's layers, forward and backward, over S Monte-Carlo samples,
     through the public operator (stag_b200.ops.stochastic_aggregate + autograd); CUDA events, features resident."""
     from stag_b200.ops import NoiseSpec
@@ -377,9 +377,46 @@ def config_row(dev, name, g, widths, S, vi, per_channel, iters, peak, warmup=3):
     ms = a.elapsed_time(b) / iters
     es = float(E) * S * len(widths)
     nbytes = sum(_bytes_per_edge_sample(N, E, D, vi) for D in widths) * E * S
-    return {"workload": name, "N": N, "E": E, "widths": list(widths), "mc_samples": S, "mode": "vi" if vi else "mle",
-            "ms_per_step": ms, "value": es / ms / 1e6, "unit": "GEdge-samples/s",
-            "frac_of_hbm_roof": nbytes / ms / 1e6 / peak, "launches_per_step": 2 * len(widths)}
+    row = {"workload": name, "N": N, "E": E, "widths": list(widths), "mc_samples": S, "mode": "vi" if vi else "mle",
+           "ms_per_step": ms, "value": es / ms / 1e6, "unit": "GEdge-samples/s",
+           "frac_of_hbm_roof": nbytes / ms / 1e6 / peak, "launches_per_step": 2 * len(widths)}
+    if graphed:
+        # launch-bound shapes: the same step captured ONCE in a CUDA graph and replayed; the device-side call counter
+        # (stag_b200.random.enable_device_counter) gives every replay fresh noise (tests/test_gpu_graphs.py)
+        try:
+            ctr = sb.random.enable_device_counter(dev)
+            ctr.zero_()
+
+            def gstep():
+                step()
+                sb.random.advance_device_counter()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    gstep()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gstep()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(iters):
+                graph.replay()
+            b.record()
+            torch.cuda.synchronize()
+            gms = a.elapsed_time(b) / iters
+            row["cuda_graph"] = {"ms_per_step": gms, "value": es / gms / 1e6, "frac_of_hbm_roof": nbytes / gms / 1e6 / peak,
+                                 "what": "the same step replayed from one captured CUDA graph, fresh noise per replay "
+                                         "(device-side Philox call counter)"}
+        except Exception as exc:   # capture problems must not take the bench line down
+            row["cuda_graph"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+        finally:
+            sb.random.disable_device_counter()
+    return row
 
 
 def _batched_graphs(sizes, edges_per_node, seed):
@@ -399,7 +436,7 @@ def configs_single_gpu(dev, peak):
     rng = np.random.default_rng(0)
     s, d = powerlaw_graph_device(2708, 10556, 0x57A6 + 1, 168, dev)
     rows["c1_cora"] = config_row(dev, "C1 Cora-shaped (N 2 708, E 10 556), 3 layers 1433-16-16, S 4", sb.Graph(s, d, 2708),
-                                 [1433, 16, 16], 4, False, False, 50, peak)
+                                 [1433, 16, 16], 4, False, False, 50, peak, graphed=True)
     s2, d2 = bench.synth_graph()
     g2 = sb.Graph(torch.from_numpy(s2), torch.from_numpy(d2), bench.N_NODES)
     rows["c2_arxiv_vi_rc"] = config_row(dev, "C2 arxiv-shaped, 3 layers, learned per-channel Normal noise (vi=True: d loc / d scale)",
@@ -408,13 +445,13 @@ def configs_single_gpu(dev, peak):
     torch.cuda.empty_cache()
     sizes = rng.integers(1000, 3500, 2)
     rows["c3_ppi_minibatch"] = config_row(dev, "C3 PPI-shaped minibatch (2 graphs), 3 layers 50-256-256, S 1 (training step)",
-                                          _batched_graphs(sizes, 28.7, 3), [50, 256, 256], 1, False, False, 50, peak)
+                                          _batched_graphs(sizes, 28.7, 3), [50, 256, 256], 1, False, False, 50, peak, graphed=True)
     sizes = rng.integers(1000, 3500, 24)
     rows["c3_ppi_all_graphs"] = config_row(dev, "C3 PPI-shaped, all 24 graphs in one batch, S 4 (inference)",
                                            _batched_graphs(sizes, 28.7, 3), [50, 256, 256], 4, False, False, 20, peak)
     sizes = np.clip(rng.normal(25.5, 12, 32), 2, 80).astype(int)
     rows["c4_molhiv_batch32"] = config_row(dev, "C4 molhiv-shaped batch of 32 molecules, 2 layers 9-16, per-channel learned Normal (vi), S 4",
-                                           _batched_graphs(sizes, 2.15, 4), [9, 16], 4, True, True, 50, peak)
+                                           _batched_graphs(sizes, 2.15, 4), [9, 16], 4, True, True, 50, peak, graphed=True)
     sizes = np.clip(rng.normal(25.5, 12, 4096), 2, 80).astype(int)
     rows["c4_molhiv_batch4096"] = config_row(dev, "C4 molhiv-shaped batch of 4 096 molecules, 2 layers 9-256, vi, S 4",
                                              _batched_graphs(sizes, 2.15, 4), [9, 256], 4, True, True, 20, peak)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define STAG_ABI_VERSION 1
+#define STAG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define STAG_API __attribute__((visibility("default")))
@@ -123,6 +123,10 @@ typedef struct StagNoise {
   const float* external; /* EXTERNAL: [S,E,K], original edge order                              */
   uint64_t seed;         /* Philox key                                                          */
   uint64_t offset;       /* Philox call counter: one per (layer, forward call)                  */
+  /* Optional DEVICE-side addend to the call counter (NULL: none): the kernels add *counter (mod 2^32) to the low
+   * word of `offset` when they run.  A training step captured in a CUDA graph bakes `offset` into its kernel
+   * parameters; bumping this device word between replays gives every replay fresh noise (ABI version 2). */
+  const uint32_t* counter;
 } StagNoise;
 
 STAG_API const char* stag_last_error(void);

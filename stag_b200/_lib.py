@@ -47,6 +47,7 @@ class StagNoise(ctypes.Structure):
         ("relu", ctypes.c_int32), ("in_norm", ctypes.c_int32), ("sample_base", ctypes.c_int32),
         ("p0", ctypes.c_void_p), ("p1", ctypes.c_void_p), ("external", ctypes.c_void_p),
         ("seed", ctypes.c_uint64), ("offset", ctypes.c_uint64),
+        ("counter", ctypes.c_void_p),   # optional device uint32 added to the call counter (CUDA-graph replays)
     ]
 
 
@@ -114,7 +115,7 @@ def load(path=None):
             fn = getattr(lib, name)  # AttributeError -> a header symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.stag_abi_version() != 1:
+        if lib.stag_abi_version() != 2:
             raise StagLibraryError("stag_b200: ABI version mismatch")
         _lib = lib
         return lib

@@ -26,6 +26,7 @@ struct KlParams {
   const float* p0;
   const float* p1;
   PhiloxKey key;
+  const uint32_t* ctr_dev;  // optional device-side addend to key.c3
   int M;
   float c_m[KL_MAX_COMPONENTS];    // log weight - log sigma - log sqrt(2 pi)
   float mu_m[KL_MAX_COMPONENTS];
@@ -69,6 +70,8 @@ __global__ void __launch_bounds__(KL_THREADS) noise_kl_kernel(const KlParams p) 
   extern __shared__ float kl_ch[];  // [KL_WARPS][2][kpad], channel-shaped gradients only
   __shared__ double red[KL_WARPS][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  PhiloxKey key = p.key;
+  if (p.ctr_dev) key.c3 += __ldg(p.ctr_dev);
   const bool ch_grads = GRADS && p.pshape == STAG_PARAM_CHANNEL;
   float* my_ch = kl_ch + (size_t)warp * 2 * p.kpad;
   if (ch_grads)
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(KL_THREADS) noise_kl_kernel(const KlParams p) 
       }
       for (int s = 0; s < p.S; ++s) {
         float raw[8];
-        raw_oct<KIND>((uint32_t)e, (uint32_t)j, (uint32_t)(p.sample_base + s), p.key, raw);
+        raw_oct<KIND>((uint32_t)e, (uint32_t)j, (uint32_t)(p.sample_base + s), key, raw);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (chan(c, i) >= p.K) continue;

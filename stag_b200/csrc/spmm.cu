@@ -80,6 +80,7 @@ struct AggParams {
   const float* p1;
   const float* ext;
   PhiloxKey key;
+  const uint32_t* ctr_dev;  // optional device-side addend to key.c3 (StagNoise::counter)
   float* norm_scale_out;
   // hub partial sums [S][num_hub_segs][dpad]
   float* part_acc;
@@ -92,6 +93,13 @@ struct AggParams {
   float* dw_ext;
   float* dp_partial;  // [grid][2][dpad]
 };
+
+// The Philox key of this launch: the host-side (seed, offset) plus the optional device-side call counter.
+__device__ __forceinline__ PhiloxKey live_key(const AggParams& p) {
+  PhiloxKey k = p.key;
+  if (p.ctr_dev) k.c3 += __ldg(p.ctr_dev);
+  return k;
+}
 
 // Channel layout of a lane: Philox block b (= lane's index among the blocks of a row) owns the two
 // quads of channels starting at c = 64*(b/8) + 4*(b%8) and at c + 32, so that the 8 lanes of a
@@ -328,6 +336,7 @@ constexpr int S3_THREADS = 256, S3_WARPS = S3_THREADS / 32;
 
 template <int KIND, int NB, bool FULL, bool INNORM>
 __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_stream_kernel(const AggParams p) {
+  const PhiloxKey key = live_key(p);
   extern __shared__ float4 ring[];
   constexpr int RS = S3_RS, NQ = 2 * NB, GW = 64 * NB, NA = 4 * NQ;
   constexpr uint32_t DATA_BYTES = s3_data_bytes(NB), WARP_BYTES = s3_warp_bytes(NB), SLOT = NQ * 512u;
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
           if (KIND != STAG_NOISE_NONE) {
 #pragma unroll
             for (int g = 0; g < NB; ++g) {
-              const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
+              const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, key.c3, p);
               q[4 * g] = r4.x; q[4 * g + 1] = r4.y; q[4 * g + 2] = r4.z; q[4 * g + 3] = r4.w;
             }
           }
@@ -631,6 +640,7 @@ __host__ __device__ constexpr uint32_t s2_warp_bytes(bool pg, int nb) {
 
 template <int KIND, int BODY, bool PG, int NB>
 __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const AggParams p) {
+  const PhiloxKey key = live_key(p);
   extern __shared__ float4 ring[];
   constexpr int RS = s2_ring_slots(PG, NB), NQ = 2 * NB, NA = 4 * NQ, GW = 64 * NB, NQS = PG ? 2 * NQ : NQ;
   constexpr int NP = NB == 1 ? 8 : 1;  // parameter (gradient) registers: per channel, or one scalar
@@ -730,7 +740,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
         if (p.kind == STAG_NOISE_EXTERNAL) {
           w = __ldg(p.ext + (int64_t)s * p.E + eid);
         } else {
-          w = transform_rt(p.kind, raw_first(p.kind, (uint32_t)eid, smp, p.key), __ldg(p.p0), p.p1 ? __ldg(p.p1) : 0.f);
+          w = transform_rt(p.kind, raw_first(p.kind, (uint32_t)eid, smp, key), __ldg(p.p0), p.p1 ? __ldg(p.p1) : 0.f);
         }
         if (p.relu) w = fmaxf(w, 0.f);
         const float A = __int_as_float(lds32(a + 8u)) * w;
@@ -813,7 +823,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
         if (BODY == 0) {
 #pragma unroll
           for (int g = 0; g < NB; ++g) {
-            const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, p.key.c3, p);
+            const uint4 r4 = philox_rk(blk0 + (uint32_t)(8 * g), (uint32_t)(ef & 0x7fffffff), smp, key.c3, p);
             const uint32_t q[4] = {r4.x, r4.y, r4.z, r4.w};
 #if STAG_PACK2
             // same operations as the scalar loop below, two words at a time on FFMA2 / FMUL2
@@ -984,6 +994,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 2) agg_stream_grads_kernel(const 
 
 template <int MODE, int KIND, int PSH, bool VEC, bool GRADS, bool FOLD>
 __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const AggParams p) {
+  const PhiloxKey key = live_key(p);
   extern __shared__ float smem[];  // param grads: [AGG_WARPS][2][dpad]
   constexpr int U = GRADS ? 1 : 2;  // edges in flight per lane
   constexpr bool GEN = MODE == 2;
@@ -1106,7 +1117,7 @@ __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const Ag
               const int64_t pi = p.pshape >= STAG_PARAM_EDGE ? my_eid : 0;
               const float a = __ldg(p.p0 + pi);
               const float b = p.p1 ? __ldg(p.p1 + pi) : 0.f;
-              my_raw = raw_first(p.kind, (uint32_t)my_eid, smp, p.key);
+              my_raw = raw_first(p.kind, (uint32_t)my_eid, smp, key);
               w = transform_rt(p.kind, my_raw, a, b);
             }
             my_pre = w;
@@ -1200,7 +1211,7 @@ __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const Ag
             } else if (fold) {
               // -------- generated per-channel noise, hot path ------------------------------------
               float w[8];
-              folded_oct<KIND>((uint32_t)ee[k], oct, smp, p.key, sa[k], sb[k], w);
+              folded_oct<KIND>((uint32_t)ee[k], oct, smp, key, sa[k], sb[k], w);
 #pragma unroll
               for (int i = 0; i < 8; ++i) acc[i] = fmaf(w[i], xv[k][i], acc[i]);
             } else {
@@ -1216,7 +1227,7 @@ __global__ void __launch_bounds__(AGG_THREADS, FOLD ? 3 : 1) agg_kernel(const Ag
 #pragma unroll
                 for (int i = 0; i < 8; ++i) pre[i] = raw[i] = w[i];
               } else {
-                raw_oct<KIND>((uint32_t)ee[k], oct, smp, p.key, raw);
+                raw_oct<KIND>((uint32_t)ee[k], oct, smp, key, raw);
                 if (PSH == 0) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) w[i] = transform<KIND>(raw[i], sa[k], sb[k]);
@@ -1472,6 +1483,7 @@ __global__ void param_finalize_kernel(const float* __restrict__ partial, int nct
 // p holds the transposed roles of stag_spmm_bwd: p.x = dout (gscale = dst_scale), p.xrow = x (rscale = src_scale).
 template <int KIND, bool VEC>
 __global__ void __launch_bounds__(256) edge_param_grads_kernel(const AggParams p) {
+  const PhiloxKey key = live_key(p);
   const int lane = threadIdx.x & 31, hl = lane & 15;
   const int64_t nhw = (int64_t)gridDim.x * (blockDim.x >> 4);
   const int64_t hw0 = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
@@ -1516,11 +1528,11 @@ __global__ void __launch_bounds__(256) edge_param_grads_kernel(const AggParams p
           }
           const uint32_t smp = (uint32_t)(p.sample_base + s);
           if (p.K == 1) {
-            const float r1 = raw_first(KIND, (uint32_t)e, smp, p.key);
+            const float r1 = raw_first(KIND, (uint32_t)e, smp, key);
 #pragma unroll
             for (int i = 0; i < 8; ++i) raw[i] = r1;
           } else {
-            raw_oct<KIND>((uint32_t)e, (uint32_t)b, smp, p.key, raw);
+            raw_oct<KIND>((uint32_t)e, (uint32_t)b, smp, key, raw);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -1568,6 +1580,7 @@ __global__ void __launch_bounds__(256) edge_param_grads_kernel(const AggParams p
 //     d loc[e] += sc sum_{s,c} x g        d scale[e] += sc sum_{s,c} x g eps
 // (eps = sqrt(2 ln 2) sqrt(-lg2 u1) cos / sin, the same variates as the forward).  4.8 ms -> see profiles/r02_modes.txt.
 __global__ void __launch_bounds__(256) edge_param_grads_fast_kernel(const AggParams p) {
+  const PhiloxKey key = live_key(p);
   const int lane = threadIdx.x & 31, sl = lane & 7;
   const int64_t ngr = (int64_t)gridDim.x * (blockDim.x >> 3);
   const int64_t g0 = (int64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
@@ -1611,7 +1624,7 @@ __global__ void __launch_bounds__(256) edge_param_grads_fast_kernel(const AggPar
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             // block 16 g + sl + 8 b: channels 64 b + 4 sl + {0..3} (slots 0..3) and 64 b + 32 + 4 sl + {0..3} (slots 4..7)
-            const uint4 r4 = philox_rk((uint32_t)(16 * g + sl + 8 * b), e, smp, p.key.c3, p);
+            const uint4 r4 = philox_rk((uint32_t)(16 * g + sl + 8 * b), e, smp, key.c3, p);
             const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int ip = 0; ip < 2; ++ip) {
@@ -1653,6 +1666,7 @@ __global__ void __launch_bounds__(256) edge_param_grads_fast_kernel(const AggPar
 // noise materialisation (compat path + RNG tests): w[s,e,c]
 template <int KIND>
 __global__ void emit_kernel(const AggParams p, float* __restrict__ w_out, float* __restrict__ eps_out) {
+  const PhiloxKey key = live_key(p);
   const int nblk = p.nblk;
   const int64_t total = (int64_t)p.S * p.E * nblk;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -1662,7 +1676,7 @@ __global__ void emit_kernel(const AggParams p, float* __restrict__ w_out, float*
     const int s = (int)(i / ((int64_t)nblk * p.E));
     const int c = first_chan(0, q);
     float raw[8];
-    raw_oct<KIND>((uint32_t)e, (uint32_t)q, (uint32_t)(p.sample_base + s), p.key, raw);
+    raw_oct<KIND>((uint32_t)e, (uint32_t)q, (uint32_t)(p.sample_base + s), key, raw);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = chan(c, j);
@@ -1699,6 +1713,7 @@ __global__ void segment_reduce_kernel(const float* __restrict__ feat, int64_t ld
 
 // noise materialisation of STAG_NOISE_NORMAL_HADAMARD: one warp per (sample, edge, 128-channel group)
 __global__ void emit_wh_kernel(const AggParams p, float* __restrict__ w_out, float* __restrict__ eps_out) {
+  const PhiloxKey key = live_key(p);
   const int lane = threadIdx.x & 31;
   const int G = p.K >> 7;
   const int64_t total = (int64_t)p.S * p.E * G;
@@ -1708,7 +1723,7 @@ __global__ void emit_wh_kernel(const AggParams p, float* __restrict__ w_out, flo
     const int64_t e = (i / G) % p.E;
     const int s = (int)(i / ((int64_t)G * p.E));
     float v[4];
-    wh_group_sums((uint32_t)e, (uint32_t)g, (uint32_t)(p.sample_base + s), p.key, lane, v);
+    wh_group_sums((uint32_t)e, (uint32_t)g, (uint32_t)(p.sample_base + s), key, lane, v);
     const int ch = 128 * g + 4 * lane;
     float w[4], z[4];
 #pragma unroll
@@ -1946,6 +1961,7 @@ static void fill_noise(AggParams& p, const StagNoise* n, int D) {
   p.p1 = n->p1;
   p.ext = n->external;
   p.key = make_key(n->seed, n->offset);
+  p.ctr_dev = n->counter;
   p.kf = 0x4B000000u;
   for (int r = 0; r < kPhiloxRounds; ++r) {
     p.rk[2 * r] = p.key.k0 + (uint32_t)r * 0x9E3779B9u;
@@ -1998,6 +2014,19 @@ static void set_shape(AggParams& p, int D, int S, int64_t gathered_rows, bool sh
     const size_t bytes = (size_t)gathered_rows * D * 4;
     ncb = (int)((bytes + kL2Operand - 1) / kL2Operand);
     if (ncb < 1) ncb = 1;
+    // a small graph with wide rows (Cora: 10 556 edges x 1 433 channels) has too few stream items to fill the chip and
+    // every item walks its edges once per 256-channel chunk: column blocks of whole 64-channel groups turn the chunks
+    // into parallel work (set_shape runs after fill_graph: p.num_items is known)
+    if (ncb == 1 && D8 >= 512) {
+      const int64_t warp_items = ((int64_t)p.num_items + p.num_hub_segs + 3) / 4 * S;
+      const int64_t slots = (int64_t)num_sms() * 16;
+      if (warp_items > 0 && warp_items < slots) {
+        const int64_t want = slots / warp_items;
+        const int64_t most = D8 / 256;
+        ncb = (int)(want < most ? want : most);
+        if (ncb < 1) ncb = 1;
+      }
+    }
     static const char* force = getenv("STAG_NCB");  // tuning knob: force the number of column blocks
     if (force && atoi(force) > 0) ncb = atoi(force);
   }
@@ -2333,6 +2362,7 @@ extern "C" int stag_noise_kl(const StagNoise* noise, int64_t num_edges, int32_t 
   p.pshape = noise->param_shape; p.relu = noise->relu; p.sample_base = noise->sample_base;
   p.p0 = noise->p0; p.p1 = noise->p1;
   p.key = make_key(noise->seed, noise->offset);
+  p.ctr_dev = noise->counter;
   p.M = prior->M;
   double wsum = 0.0;
   for (int m = 0; m < prior->M; ++m) {

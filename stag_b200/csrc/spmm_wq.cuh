@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggPar
   const uint32_t tmem0 = tmem_base_s;
   const uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint64_t h_desc = tc_desc(h_s), a_desc = tc_desc(at_s);
+  const PhiloxKey key = live_key(p);
   uint32_t mma_count = 0;  // MMA chains issued so far by this CTA (every thread counts): mbarrier = count & 1, parity = (count >> 1) & 1
 
   const int G = p.D >> 7;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggPar
       uint4 v[NBLK];
 #pragma unroll
       for (int i = 0; i < NBLK; ++i) {
-        v[i] = philox_rk(blk, eid[i] & 0x7fffffffu, smp, p.key.c3, p);
+        v[i] = philox_rk(blk, eid[i] & 0x7fffffffu, smp, key.c3, p);
         v[i].x = (v[i].x & kWhAnd) | kWhOr; v[i].y = (v[i].y & kWhAnd) | kWhOr;
         v[i].z = (v[i].z & kWhAnd) | kWhOr; v[i].w = (v[i].w & kWhAnd) | kWhOr;
       }

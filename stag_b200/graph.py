@@ -319,17 +319,18 @@ def rand_graph(num_nodes, num_edges, idtype=None, device=None):
 
 
 def batch(graphs):
-    """Block-diagonal batching (dgl.batch); records batch_num_nodes / batch_num_edges."""
+    """Block-diagonal batching (dgl.batch); records batch_num_nodes / batch_num_edges.  Runs on the device the
+    graphs live on: one concatenation of the edge lists and one repeat_interleave of the node offsets, no per-graph
+    arithmetic (a molhiv minibatch is 32-128 graphs of ~25 nodes: scripts/molhiv_mle/run.py builds one per step)."""
     graphs = [as_graph(g) for g in graphs]
-    off, srcs, dsts = 0, [], []
-    for g in graphs:
-        s, d = g.edges()
-        srcs.append(s + off)
-        dsts.append(d + off)
-        off += g.number_of_nodes()
-    st = _Structure(torch.cat(srcs), torch.cat(dsts), off,
-                    torch.tensor([g.number_of_nodes() for g in graphs], dtype=torch.int64),
-                    torch.tensor([g.number_of_edges() for g in graphs], dtype=torch.int64))
+    dev = graphs[0].device if graphs else torch.device("cpu")
+    nn_ = torch.tensor([g.number_of_nodes() for g in graphs], dtype=torch.int64)
+    ne_ = torch.tensor([g.number_of_edges() for g in graphs], dtype=torch.int64)
+    off = torch.cumsum(nn_, 0) - nn_                                  # first node id of every graph
+    eoff = torch.repeat_interleave(off.to(dev), ne_.to(dev))          # [E] offset of every edge's graph
+    srcs = torch.cat([g._s.src for g in graphs]) + eoff if graphs else torch.empty(0, dtype=torch.int64)
+    dsts = torch.cat([g._s.dst for g in graphs]) + eoff if graphs else torch.empty(0, dtype=torch.int64)
+    st = _Structure(srcs, dsts, int(nn_.sum()), nn_, ne_)
     out = Graph(_structure=st)
     for k in graphs[0].ndata.keys():
         out.ndata[k] = torch.cat([g.ndata[k] for g in graphs], 0)

@@ -165,6 +165,10 @@ def _fill_noise(spec, kind, K, p0, p1, ext, relu, in_norm, sample_base, seed, of
     n.relu, n.in_norm, n.sample_base = int(relu), int(in_norm), int(sample_base)
     n.p0, n.p1, n.external = _ptr(p0), _ptr(p1), _ptr(ext)
     n.seed, n.offset = seed, offset
+    # device-side addend to the call counter (stag_b200.random.enable_device_counter): a step captured in a CUDA graph
+    # draws fresh noise on every replay
+    ctr = _random.device_counter(p0.device if p0 is not None else (ext.device if ext is not None else None))
+    n.counter = 0 if ctr is None else ctr.data_ptr()
     return n
 
 
@@ -406,6 +410,22 @@ def stochastic_aggregate(graph, feat, edge_weight=None, reduce="sum", src_scale=
                    sample_base=spec.sample_base, seed=spec.seed, offset=spec.offset,
                    param_shape=spec.param_shape)
         p0, p1 = spec.p0, spec.p1
+        pad = (-D) % 4
+        if pad and D > 128 and not spec.in_norm and spec.param_shape != _lib.PARAM_EDGE_CHANNEL:
+            # A width that is not a multiple of 4 (Cora's 1433) has rows that are not 16-byte aligned, which leaves only
+            # the scalar-guarded kernels.  Zero-padded channels contribute nothing and the variate of a channel depends
+            # on (edge, channel, sample) only, so the padded problem has the same first D outputs and gradients; the
+            # pad / slice pair is differentiable torch.  (Narrow rows -- PPI's 50, molhiv's 9 -- are launch-bound: the
+            # two extra launches cost more than the vector loads save, measured.)
+            Dp = D + pad
+            featp = torch.nn.functional.pad(feat, (0, pad))
+            if spec.K == D:
+                cfg["K"] = Dp
+                if spec.param_shape == _lib.PARAM_CHANNEL:
+                    p0 = torch.nn.functional.pad(p0, (0, pad))
+                    p1 = None if p1 is None else torch.nn.functional.pad(p1, (0, pad), value=1.0)
+            out = _StochasticSpMM.apply(featp, p0, p1, None, cfg)[..., :D]
+            return out[0] if squeeze else out
     else:
         w = edge_weight
         _require_cuda(w, "edge_weight")

@@ -1,10 +1,11 @@
 """``GAT`` -- constructor and forward of the reference's ``stag.zoo.GAT`` (stag/zoo/gat.py:7-149).
-The noise ``[E,H]`` multiplies the pre-softmax logits (:117-119); the edge softmax is a
-different hot loop (segmented softmax) and is OUT OF SCOPE for the fused kernels
-(SURVEY.md 8(f).2): logits/softmax run as torch ops on the device, the final weighted
-aggregation ``update_all(u_mul_e('ft','a'), sum)`` (:125-126) runs on ``stag_spmm_fwd``.
-``accepts_noise_spec`` is False, so ``StagLayer`` hands this layer a tensor emitted from the
-library's Philox stream.
+The noise ``[E,H]`` multiplies the pre-softmax logits (:117-119).  The segmented softmax over the in-edges of each
+node runs on ``stag_edge_softmax`` (forward and backward in one fused pass each, csrc/edge_softmax.cu) and the final
+weighted aggregation ``update_all(u_mul_e('ft','a'), sum)`` (:125-126) on ``stag_spmm_fwd`` with the attention as
+external weights (all heads in one launch while the expanded ``[E, H*F]`` weights stay below 256 MB, else one
+launch per head).  The logits and the noise product are elementwise torch ops on ``[E,H]``.
+``accepts_noise_spec`` is False: the noise multiplies the LOGITS, not the messages, so ``StagLayer`` hands this
+layer a tensor emitted from the library's Philox stream (``stag_noise_emit``, K = num_heads).
 """
 import torch
 from torch import nn

@@ -22,7 +22,7 @@ def test_library_exports_every_header_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), "header declares %s but the library does not export it" % s
     assert sorted(_lib.SIGNATURES) == syms, "ctypes binding and header disagree"
-    assert lib.stag_abi_version() == 1
+    assert lib.stag_abi_version() == 2
     assert lib.stag_hub_threshold() > 0 and lib.stag_hub_segment() > 0
 
 
@@ -30,7 +30,7 @@ def test_struct_layout_matches_header():
     import ctypes
     from stag_b200 import _lib
     assert ctypes.sizeof(_lib.StagGraph) == 112
-    assert ctypes.sizeof(_lib.StagNoise) == 64
+    assert ctypes.sizeof(_lib.StagNoise) == 72
 
 
 def test_argument_errors_are_reported_not_thrown(lib):
