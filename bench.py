@@ -417,7 +417,7 @@ def run_ours(args, rank, world):
             roof["rng_ceiling"] = {"normals_per_launch": normals, "achieved_normals_per_s": normals / (avg_ms * 1e-3),
                                    "xu_peak_normals_per_s": xu_peak, "frac": normals / (avg_ms * 1e-3) / xu_peak,
                                    "note": "Box-Muller, 2 MUFU per normal, 16 MUFU lanes/clk/SM measured"}
-    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
             roof["traffic"] = json.load(f).get(dom)

@@ -75,7 +75,7 @@ cases = [
     ("backward dX + d(loc,scale), scalar params (vi)", lambda: bwd(noise(L.NOISE_NORMAL, D, L.PARAM_SCALAR, one, sg)), bench.bytes_bwd(S, True, False)),
     ("Normal, per-channel noise, per-edge params [E,1] (amortised re)", lambda: fwd(noise(L.NOISE_NORMAL, D, L.PARAM_EDGE, loc_e, sg_e)), bench.bytes_fwd(S, False) + 8 * E),
     ("backward dX + d(loc,scale)[E,1], 16 samples in one call (amortised re)", lambda: bwd_edge(noise(L.NOISE_NORMAL, D, L.PARAM_EDGE, loc_e, sg_e)), bench.bytes_bwd(S, True, False) + 16 * E),
-    ("Normal via tensor-core Hadamard generator (opt-in)", lambda: fwd(noise(L.NOISE_NORMAL_HADAMARD, D, L.PARAM_SCALAR, one, sg)), bench.bytes_fwd(S, False)),
+    ("Normal via tensor-core Hadamard generator (default where eligible)", lambda: fwd(noise(L.NOISE_NORMAL_HADAMARD, D, L.PARAM_SCALAR, one, sg)), bench.bytes_fwd(S, False)),
 ]
 rows = []
 for name, fn, nbytes in cases:
