@@ -250,10 +250,13 @@ __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggPar
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        __threadfence_block();
-        if (atomicAdd(&arrive_cnt[mma_count & 1u], 1) == NW - 1) {
-          arrive_cnt[mma_count & 1u] = 0;  // next used two rounds on, after the MMAs issued here have completed
-          __threadfence_block();
+        // one acq_rel read-modify-write instead of fence + atomic + fence: a MEMBAR.CTA costs ~190 cycles with the 8
+        // tile stores of the round in flight, and the other 31 lanes of the warp wait for lane 0 at the reconvergence
+        uint32_t old;
+        const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(&arrive_cnt[mma_count & 1u]);
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_s) : "memory");
+        if (old == NW - 1) {
+          asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(cnt_s), "r"(0u) : "memory");  // next used two rounds on
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           issue_mma();
         }
