@@ -87,6 +87,7 @@ struct GemmParams {
   float* out;
   int64_t ldo;
   uint32_t tmem_cols;
+  int ksplit;  // > 1: a cluster of ksplit CTAs (blockIdx.x) shares one row tile (blockIdx.y), each taking a range of K blocks
 };
 
 // store one 16-byte chunk (4 floats) of row r, chunk index ch (0..7) of a [rows][32] tile, split hi/lo
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * GM;
+  const int krank = p.ksplit > 1 ? (int)blockIdx.x : 0;
+  const int64_t m0 = (int64_t)(p.ksplit > 1 ? blockIdx.y : blockIdx.x) * GM;
   const bool vec_a = (p.lda % 4 == 0) && (((uintptr_t)p.a & 15) == 0);
   const bool vec_w = (p.ldw % 4 == 0) && (((uintptr_t)p.wt & 15) == 0);
   const bool vec_o = (p.ldo % 4 == 0) && (((uintptr_t)p.out & 15) == 0);
@@ -167,8 +169,9 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
       vw[j] = load_row4(p.wt, p.ldw, i < p.npad * 8 ? (i >> 3) : p.Nout, p.Nout, k0 + (i & 7) * 4, p.K, vec_w);
     }
   };
-  load_tiles(0);
-  for (int kb = 0; kb < nkb; ++kb) {
+  const int kb_lo = p.ksplit > 1 ? krank * nkb / p.ksplit : 0, kb_hi = p.ksplit > 1 ? (krank + 1) * nkb / p.ksplit : nkb;
+  load_tiles(kb_lo);
+  for (int kb = kb_lo; kb < kb_hi; ++kb) {
     const int k0 = kb * GK;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
 #pragma unroll
       for (int ks = 0; ks < GK / 8; ++ks) {
         const uint64_t adv = (uint64_t)(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16 B along K
-        mma_tf32(tmem_d, dah + adv, dwh + adv, idesc, (kb | ks) != 0);
+        mma_tf32(tmem_d, dah + adv, dwh + adv, idesc, ((kb - kb_lo) | ks) != 0);
         mma_tf32(tmem_d, dal + adv, dwh + adv, idesc, 1);
         mma_tf32(tmem_d, dah + adv, dwl + adv, idesc, 1);
       }
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
                        smem_u32(&mma_bar))
                    : "memory");
     }
-    if (kb + 1 < nkb) load_tiles(kb + 1);
+    if (kb + 1 < kb_hi) load_tiles(kb + 1);
     // the shared tiles may be overwritten (and, after the last block, TMEM read) once the MMAs are done
     mbar_wait(&mma_bar, phase);
     phase ^= 1;
@@ -219,9 +222,40 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
   // TMEM gives a thread one row x 32 columns; a per-warp shared scratch (pitch 33) transposes that so
   // that every store instruction writes four full 128-byte row segments
   float* scratch = a_hi + warp * (32 * 33);  // the operand tiles are free now
+  // split-K (small M, long K: Cora's 2 708 x 1 433 x 16 is 22 row tiles of 45 K blocks): the CTAs of a cluster hold
+  // partial accumulators of ONE row tile.  Ranks > 0 write theirs into rank 0's shared memory (DSMEM), rank 0 adds
+  // them in rank order -- deterministic -- and runs the epilogue.
+  float* part = a_hi + 4 * (32 * 33) + 32;  // [ksplit - 1][128][npad] behind the scratch (rank 0's copy is the target)
+  if (p.ksplit > 1) {
+    // every CTA of the cluster is done with its MMAs: rank 0's operand tiles may be overwritten
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (krank > 0) {
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(part)), "r"(0));
+      remote += (uint32_t)(((krank - 1) * GM + warp * 32 + lane) * p.npad) * 4u;
+      for (int n0 = 0; n0 < p.npad; n0 += 16) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)(n0 + j) * 4u), "r"(v[j]),
+                       "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                       : "memory");
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   const int64_t row = m0 + warp * 32 + lane;
   const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.0f;
-  for (int n0 = 0; n0 < p.npad; n0 += 32) {
+  for (int n0 = 0; n0 < p.npad && krank == 0; n0 += 32) {
     uint32_t v[32];
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0;
     asm volatile(
@@ -235,6 +269,19 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int r = 1; r < p.ksplit; ++r) {   // the other ranks' partial sums of this row, in rank order
+      const float* pr = part + (size_t)((r - 1) * GM + warp * 32 + lane) * p.npad + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (n0 + j < p.npad) {
+          const float4 t = *reinterpret_cast<const float4*>(pr + j);
+          v[j] = __float_as_uint(__uint_as_float(v[j]) + t.x);
+          v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + t.y);
+          v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + t.z);
+          v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + t.w);
+        }
+      }
+    }
     __syncwarp();  // the previous chunk's readers are done with the scratch
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -643,6 +690,10 @@ extern "C" int stag_gemm_tcgen05(const float* a, int64_t lda, const float* wt, i
         const int tiles = (int)((227 * 1024 - 1024 - fixed) / G2_TILE);   // 1 KB for the static barriers
         q.nlo = tiles >= 8 ? 3 : 2;
         q.nst = (uint32_t)(tiles - (int)q.nlo < G2_MAXST ? tiles - (int)q.nlo : G2_MAXST);
+        static const char* e_nlo = getenv("STAG_G2_NLO");
+        static const char* e_nst = getenv("STAG_G2_NST");
+        if (e_nlo) { q.nlo = (uint32_t)atoi(e_nlo); q.nst = (uint32_t)(tiles - (int)q.nlo < G2_MAXST ? tiles - (int)q.nlo : G2_MAXST); }
+        if (e_nst && (uint32_t)atoi(e_nst) < q.nst) q.nst = (uint32_t)atoi(e_nst);
         const size_t smem2 = fixed + (size_t)(q.nst + q.nlo) * G2_TILE;
         STAG_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         const int64_t grid2 = q.ntiles < num_sms() ? q.ntiles : num_sms();
@@ -663,6 +714,33 @@ extern "C" int stag_gemm_tcgen05(const float* a, int64_t lda, const float* wt, i
   STAG_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = (M + GM - 1) / GM;
   STAG_CHECK_ARG(grid < (1ll << 31), "stag_gemm_tcgen05: too many row tiles");
+  // few row tiles and a long K: split K over a cluster (at most 8 CTAs, two K blocks or more each, partial tiles
+  // within the 79 KB behind the epilogue scratch)
+  const int nkb = (K + GK - 1) / GK;
+  int ksplit = 1;
+  static const char* e_ks = getenv("STAG_GEMM_KSPLIT");
+  if (grid * 2 <= num_sms() && nkb >= 4 && grid < 65536) {
+    ksplit = (int)(2 * num_sms() / grid);
+    if (ksplit > 8) ksplit = 8;
+    if (ksplit > nkb / 2) ksplit = nkb / 2;
+    if (ksplit > 158 / p.npad + 1) ksplit = 158 / p.npad + 1;
+    if (e_ks && atoi(e_ks) >= 1 && atoi(e_ks) < ksplit) ksplit = atoi(e_ks);
+  }
+  p.ksplit = ksplit;
+  if (ksplit > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ksplit, (unsigned)grid, 1);
+    cfg.blockDim = dim3(GTHREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ksplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    STAG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p));
+    STAG_LAUNCH_CHECK();
+    return STAG_OK;
+  }
   gemm_tcgen05_kernel<<<(unsigned)grid, GTHREADS, smem, stream>>>(p);
   STAG_LAUNCH_CHECK();
   return STAG_OK;
