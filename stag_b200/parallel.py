@@ -241,7 +241,15 @@ class RowPartition:
             return dx
         back = torch.empty((int(sum(self.send_counts)), D), dtype=dx_ext.dtype, device=dx_ext.device)
         _all_to_all_rows(back, dx_ext[self.n_own:].contiguous(), self.send_counts, self.recv_counts, group=self.group)
-        dx.index_add_(0, self.send_idx, back)
+        # a peer asks for every row at most once, so its segment is a plain gather-add-scatter (no atomics: an
+        # index_add_ over the 1.2 M x 100 halo of the products shape took 9 of the 10.7 ms of this call); segments
+        # in peer order: deterministic
+        off = 0
+        for c in self.send_counts:
+            if c:
+                idx = self.send_idx[off:off + c]
+                dx.index_copy_(0, idx, dx.index_select(0, idx).add_(back[off:off + c]))
+            off += c
         return dx
 
     # ---- whole-block form (halo=False) --------------------------------------------------------------------------
