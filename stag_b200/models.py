@@ -73,7 +73,13 @@ class StagModel(torch.nn.Module):
     def _forward_samples(self, graph, feat, n_samples, sample_base=0):
         """[S, N, C] outputs of S Monte-Carlo passes (sample s uses Philox sample index
         ``sample_base + s``)."""
-        if n_samples == 1 or not self._can_batch() or feat.device.type != "cuda":
+        batched = self._can_batch() and feat.device.type == "cuda"
+        if sample_base != 0 and not batched:
+            # sequential passes take a fresh Philox call counter each and always draw sample index 0: ranks sharing a
+            # seed would all draw the SAME noise
+            raise NotImplementedError("sample_base (Monte-Carlo samples sharded over ranks) needs the sample-batched "
+                                      "path: fused base layers on a CUDA device")
+        if (n_samples == 1 and sample_base == 0) or not batched:
             return torch.stack([self._forward(graph, feat) for _ in range(n_samples)], dim=0)
         graph = as_graph(graph).local_var()
         h = feat  # [N,D] shared by all samples until the first stochastic layer

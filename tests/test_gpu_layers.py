@@ -249,3 +249,32 @@ def test_edge_softmax_matches_the_scatter_formulation(H):
     ref.backward(gout.double())
     assert rel(a.grad, b.grad) < 1e-5
     assert stag.ops.edge_softmax(g, logits[:, 0]).shape == (E,)
+
+
+def test_sample_shards_draw_their_own_sample_indices():
+    """Monte-Carlo samples sharded over ranks (emulated on one GPU): with a common seed the shards [base, base + n)
+    concatenate to the unsharded result bitwise -- also shards of ONE sample, which must not fall back to sequential
+    passes (those always draw sample index 0)."""
+    import stag_b200 as stag
+    from stag_b200 import parallel as P
+    rng = np.random.default_rng(0)
+    N, E, S = 3000, 20000, 4
+    g = stag.Graph(torch.from_numpy(rng.integers(0, N, E)), torch.from_numpy(rng.integers(0, N, E)), N).to("cuda")
+    x = torch.from_numpy(rng.standard_normal((N, 32)).astype(np.float32)).cuda()
+    torch.manual_seed(0)
+    mk = lambda d: torch.distributions.Normal(torch.ones(d), 0.3 * torch.ones(d))  # noqa: E731
+    layers = torch.nn.ModuleList([
+        stag.layers.StagLayer(stag.zoo.GCN(32, 64, activation=torch.relu), q_a=mk(32), p_a=mk(32), vi=True),
+        stag.layers.StagLayer(stag.zoo.GCN(64, 10), q_a=mk(64), p_a=mk(64), vi=True),
+    ]).cuda()
+    model = stag.models.StagModel(layers, kl_scaling=0.1)
+    stag.manual_seed(5)
+    full = model._forward_samples(g, x, S, sample_base=0).detach()
+    assert not torch.equal(full[0], full[1])
+    for world in (2, 4):
+        parts = []
+        for rank in range(world):
+            base, n = P.shard_samples(S, rank, world)
+            stag.manual_seed(5)
+            parts.append(model._forward_samples(g, x, n, sample_base=base).detach())
+        assert torch.equal(torch.cat(parts), full), world

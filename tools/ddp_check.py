@@ -22,7 +22,7 @@ from stag_b200 import parallel as P
 
 
 def rel(a, b):
-    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp(min=1e-30))
+    return float((a.detach().double() - b.detach().double()).abs().max() / b.detach().double().abs().max().clamp(min=1e-30))
 
 
 def build(seed=0):
