@@ -59,6 +59,30 @@ def test_split_k_cluster(M, K, N):
     assert rel(plain, a.double() @ w.double()) < 1e-5
 
 
+@pytest.mark.parametrize("M,K,N", [(300001, 128, 128), (300001, 128, 40), (250000, 160, 64), (200003, 100, 121),
+                                   (190000, 96, 16), (150000, 32, 256), (400000, 64, 7), (169343 * 4, 128, 128)])
+def test_persistent_tma_form_many_tiles_per_cta(M, K, N):
+    """Row counts far beyond 148 x 128: every CTA of the persistent TMA form walks many row tiles, so its rings (sizes that
+    do not divide the K blocks of a tile), both TMEM accumulators and every mbarrier phase wrap many times.  Ragged M,
+    K tails filled by the TMA unit, N from one MMA column block to the 256-column maximum; fused epilogue; elementwise
+    tolerance against float64; bitwise run-to-run."""
+    from stag_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g, device="cuda")
+    w = torch.randn(K, N, generator=g, device="cuda")
+    b = torch.randn(N, generator=g, device="cuda")
+    rs = torch.rand(M, generator=g, device="cuda") + 0.5
+    out = ops.dense_transform(a, w, row_scale=rs, bias=b, relu=True)
+    ref = torch.relu((a.double() @ w.double()) * rs.double()[:, None] + b.double())
+    scale = float(ref.abs().max())
+    assert bool(((out.double() - ref).abs() <= 1e-5 * ref.abs() + 2e-6 * scale).all())
+    assert torch.equal(out, ops.dense_transform(a, w, row_scale=rs, bias=b, relu=True))
+    del out, ref
+    plain = ops.dense_transform(a, w)
+    ref = a.double() @ w.double()
+    assert bool(((plain.double() - ref).abs() <= 1e-5 * ref.abs() + 2e-6 * float(ref.abs().max())).all())
+
+
 def test_gradients():
     from stag_b200 import ops
     g = torch.Generator().manual_seed(1)
