@@ -81,7 +81,12 @@ __device__ __forceinline__ void stg256cs(char* dst, const float2* v) {
 
 // NW warps; XB units of the register ring (XB divides the 8 / NW * 2 units of a round: the slot of a unit must not
 // depend on the round); DB double-buffered TMEM; MINB CTAs per SM
-template <int NW, int XB, bool DB, int MINB>
+// GMODE: where the registers of a consumed unit get their next gather: 0 after each edge, 1 after the unit (4 LDG.256
+//        back to back: 1 % faster), 2 all 16 of a round at its end (as fast: the ring needs ~1 500 cycles of flight time,
+//        which the Philox phase of the next round provides; a half-round ring, XB = 2, does not: 1.8 - 2.0 ms)
+// LATE_REC: the records / rows / next neighbours of a round are read from the ring AFTER the Philox phase of the next round
+//        instead of before it (24 registers fewer live across it: 1.47 -> 1.43 ms)
+template <int NW, int XB, bool DB, int MINB, int GMODE = 0, bool LATE_REC = false>
 __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggParams p) {
   constexpr int NCH = 8 / NW;     // channel halves per thread
   constexpr int NU = 2 * NCH;     // units (edge pair, channel half) per round
@@ -300,16 +305,20 @@ __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggPar
       cp_async_commit();
       int4 rc4[4];  // records of this round's edges
       uint32_t ro4[4];
+      auto read_records = [&]() {
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) rc4[k4] = lds128(rec_g + (((uint32_t)(WQ_EPR * r + k4) & rmask) << 4));
+        for (int k4 = 0; k4 < 4; ++k4) rc4[k4] = lds128(rec_g + (((uint32_t)(WQ_EPR * r + k4) & rmask) << 4));
 #pragma unroll
-      for (int k4 = 0; k4 < 4; ++k4) ro4[k4] = (uint32_t)lds32(row_g + (((uint32_t)(WQ_EPR * r + k4) & rmask) << 2));
-      neighbours(r + 1, un1);
+        for (int k4 = 0; k4 < 4; ++k4) ro4[k4] = (uint32_t)lds32(row_g + (((uint32_t)(WQ_EPR * r + k4) & rmask) << 2));
+        neighbours(r + 1, un1);
+      };
+      if (!LATE_REC) read_records();
       const uint32_t done = mma_count - 1u;
       tc_mbar_wait(bar_s + 8u * (done & 1u), (done >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem0 + ((uint32_t)(32 * wq) << 16) + (DB ? (done & 1u) * 128u : 0u) + (uint32_t)(64 * ch0);
       if (DB && r + 1 < rounds) bytes_and_mma(r + 1);  // the MMAs of round r have read the A tile; the other accumulator was read out before the barrier
+      if (LATE_REC) read_records();
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
         const int hf = u / NCH, chl = u % NCH;
@@ -345,13 +354,28 @@ __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggPar
               }
             }
           }
-          {
+          if (GMODE == 0) {
             // the registers just consumed take the same edge of unit u + XB (of this round or the next)
             const int nu = (u + XB) % NU;
             const uint32_t un = (u + XB) < NU ? (uint32_t)rc4[2 * (nu / NCH) + kk].x : un1[2 * (nu / NCH) + kk];
             load_half(un, nu % NCH, xu + 4 * kk);
           }
         }
+        if (GMODE == 1) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int nu = (u + XB) % NU;
+            const uint32_t un = (u + XB) < NU ? (uint32_t)rc4[2 * (nu / NCH) + kk].x : un1[2 * (nu / NCH) + kk];
+            load_half(un, nu % NCH, xu + 4 * kk);
+          }
+        }
+      }
+      if (GMODE == 2) {
+        static_assert(GMODE != 2 || XB == NU, "round-end gathers need a whole round in the ring");
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) load_half(un1[2 * (u / NCH) + kk], u % NCH, xb[u] + 4 * kk);
       }
       if (!DB && r + 1 < rounds) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -373,7 +397,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggPar
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(TM_COLS) : "memory");
 }
 
-template <int NW, int XB, bool DB, int MINB>
+template <int NW, int XB, bool DB, int MINB, int GMODE = 0, bool LATE_REC = false>
 static int launch_wh_quad_inst(const AggParams& p, cudaStream_t stream) {
   const int64_t total = (int64_t)((p.num_hub_segs + p.num_items + WQ_GROUPS - 1) / WQ_GROUPS) * p.S * (p.D >> 7);
   const int64_t cap = (int64_t)num_sms() * MINB;
@@ -382,8 +406,8 @@ static int launch_wh_quad_inst(const AggParams& p, cudaStream_t stream) {
   constexpr int max_ctas = DB ? 2 : 4;
   const size_t pad = (size_t)(227 * 1024) / (max_ctas + 1) + 1024;
   const size_t smem = wq_smem(NW) > pad ? wq_smem(NW) : pad;
-  STAG_CUDA(cudaFuncSetAttribute(agg_wh_quad_kernel<NW, XB, DB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  agg_wh_quad_kernel<NW, XB, DB, MINB><<<grid, 32 * NW, smem, stream>>>(p);
+  STAG_CUDA(cudaFuncSetAttribute(agg_wh_quad_kernel<NW, XB, DB, MINB, GMODE, LATE_REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  agg_wh_quad_kernel<NW, XB, DB, MINB, GMODE, LATE_REC><<<grid, 32 * NW, smem, stream>>>(p);
   STAG_LAUNCH_CHECK();
   return STAG_OK;
 }
@@ -398,10 +422,14 @@ static int launch_wh_quad(const AggParams& p, cudaStream_t stream) {
   static const char* var = getenv("STAG_WQ_VARIANT");
   const int v = var ? atoi(var) : 0;
   switch (v) {
-    case 1: return launch_wh_quad_inst<4, 4, false, 2>(p, stream);
+    case 1: return launch_wh_quad_inst<4, 4, false, 2, 1>(p, stream);
     case 2: return launch_wh_quad_inst<4, 2, false, 3>(p, stream);
     case 3: return launch_wh_quad_inst<8, 2, true, 2>(p, stream);
-    default: return launch_wh_quad_inst<4, 4, true, 2>(p, stream);
+    case 4: return launch_wh_quad_inst<4, 4, true, 2, 0>(p, stream);   // gathers re-issued per edge (the default until late r02)
+    case 5: return launch_wh_quad_inst<4, 4, true, 2, 2>(p, stream);   // all gathers of a round at its end
+    case 6: return launch_wh_quad_inst<4, 4, true, 2, 1, false>(p, stream);  // records read before the Philox phase
+    case 7: return launch_wh_quad_inst<4, 4, true, 2, 2, true>(p, stream);
+    default: return launch_wh_quad_inst<4, 4, true, 2, 1, true>(p, stream);
   }
 }
 
