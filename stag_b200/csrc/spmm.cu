@@ -220,6 +220,7 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, in
   // 2 = like 0 with sqrt(2 ln 2) folded into B of Normal noise (agg_stream3_kernel takes sqrt(-lg2 u1) as radius)
   // 3 = like 0 with the variance constant of the Hadamard mix folded into B (agg_wh_stream_kernel)
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (scales_only == 3 && j == 0) reinterpret_cast<int*>(rec + p.E)[0] = 0;  // the work queue of agg_wh_quad_kernel (spare slot behind the records)
   if (j >= p.E) return;
   const int idx = __ldg(p.indices + j);
   const int ef = __ldg(p.eidf + j);

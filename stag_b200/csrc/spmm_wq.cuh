@@ -165,7 +165,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggPar
   const uint32_t mk_rec = rec_base + (uint32_t)(8 * warp + (lane >> 3)) * WQ_REC_STRIDE + 4u;
   const uint32_t mk_row = at_s + (uint32_t)(32 * wq + rb + (lane >> 3)) * 128u;
 
-  for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+  // CTA items are handed out by a queue (a counter behind the edge records, zeroed by edge_record_kernel): they differ in
+  // length (1 .. 47 rounds at the arxiv shape), a static stride left the slowest CTA 10 - 13 % more rounds than the
+  // average (tools/item_balance.py).  The next index is fetched while the current item runs.
+  __shared__ int item_s;
+  int* const queue = reinterpret_cast<int*>(const_cast<int4*>(p.rec) + p.E);
+  if (tid == 0) item_s = atomicAdd(queue, 1);
+  __syncthreads();
+  for (;;) {
+    const int64_t item = item_s;
+    if (item >= total) break;
     const int64_t outer = item / IG;
     const int gi = (int)(item - outer * IG) * WQ_GROUPS + 8 * wq + jq;
     const int cg = (int)(outer % G), s = (int)(outer / G);
@@ -191,8 +200,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) agg_wh_quad_kernel(const AggPar
     int maxn = nedges;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(0xffffffffu, maxn, o));
-    __syncthreads();  // the previous item's readers of maxn_s are done
+    __syncthreads();  // the previous item's readers of maxn_s are done, and everyone has read item_s
     if (lane == 0) maxn_s[warp] = maxn;
+    if (tid == 0) item_s = atomicAdd(queue, 1);
     __syncthreads();
     maxn = max(max(maxn_s[0], maxn_s[1]), max(maxn_s[2], maxn_s[3]));  // warps 4..7 walk the items of warps 0..3
     const int rounds = (maxn + WQ_EPR - 1) / WQ_EPR;
@@ -413,10 +423,14 @@ static int launch_wh_quad_inst(const AggParams& p, cudaStream_t stream) {
 }
 
 static int launch_wh_quad(const AggParams& p, cudaStream_t stream) {
-  if (p.E > 0) {
+  if (p.E > 0) {   // also zeroes the work queue behind the records
     edge_record_kernel<STAG_NOISE_NORMAL><<<(unsigned)((p.E + 255) / 256), 256, 0, stream>>>(p, const_cast<int4*>(p.rec), 3);
     STAG_LAUNCH_CHECK();
+  } else {
+    STAG_CUDA(cudaMemsetAsync(const_cast<int4*>(p.rec), 0, 16, stream));
   }
+  STAG_CHECK_ARG((int64_t)((p.num_hub_segs + p.num_items + WQ_GROUPS - 1) / WQ_GROUPS) * p.S * (p.D >> 7) < (1ll << 30),
+                 "stag_spmm: too many work items for one launch");
   // XB = 4 (a whole round of gathered rows in flight per lane) with two TMEM accumulators is the fastest measured
   // form (profiles/r02_wq_forms.txt); STAG_WQ_VARIANT selects the others for A/B runs
   static const char* var = getenv("STAG_WQ_VARIANT");
