@@ -220,7 +220,7 @@ __global__ void edge_record_kernel(const AggParams p, int4* __restrict__ rec, in
   // 2 = like 0 with sqrt(2 ln 2) folded into B of Normal noise (agg_stream3_kernel takes sqrt(-lg2 u1) as radius)
   // 3 = like 0 with the variance constant of the Hadamard mix folded into B (agg_wh_stream_kernel)
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (scales_only == 3 && j == 0) reinterpret_cast<int*>(rec + p.E)[0] = 0;  // the work queue of agg_wh_quad_kernel (spare slot behind the records)
+  if (scales_only >= 2 && j == 0) reinterpret_cast<int*>(rec + p.E)[0] = 0;  // the work queue of agg_stream_kernel / agg_wh_quad_kernel (spare slot behind the records)
   if (j >= p.E) return;
   const int idx = __ldg(p.indices + j);
   const int ef = __ldg(p.eidf + j);
@@ -361,7 +361,18 @@ __global__ void __launch_bounds__(S3_THREADS, s3_min_blocks(NB, INNORM)) agg_str
   const int64_t total = (int64_t)IG * p.S * p.ncb;
   const int64_t total_warps = (int64_t)gridDim.x * S3_WARPS;
 
-  for (int64_t item = (int64_t)blockIdx.x * S3_WARPS + warp; item < total; item += total_warps) {
+  // warp items come from a queue (a counter behind the edge records, zeroed by edge_record_kernel): they differ in
+  // length, and with a static stride the slowest warp had ~10 % more edges than the average (tools/item_balance.py).
+  // The next index is requested before the current item is walked.
+  int* const queue = reinterpret_cast<int*>(const_cast<int4*>(p.rec) + p.E);
+  int64_t item;
+  {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(queue, 1);
+    item = __shfl_sync(0xffffffffu, v, 0);
+  }
+  for (int nxt = 0; item < total; item = __shfl_sync(0xffffffffu, nxt, 0)) {
+    if (lane == 0) nxt = atomicAdd(queue, 1);
     const int64_t outer = item / IG;
     const int gi = (int)(item - outer * IG) * RPW + sub;
     int s, cb;
@@ -1840,9 +1851,12 @@ static int launch_stream_inst(const AggParams& q, cudaStream_t stream) {
   const int64_t cap = (int64_t)num_sms() * s3_min_blocks(NB, INNORM);
   const int grid = (int)(nctas < 1 ? 1 : (nctas < cap ? nctas : cap));
   const size_t smem = (size_t)S3_WARPS * s3_warp_bytes(NB);
-  if (q.E > 0) {
+  STAG_CHECK_ARG(witems < (1ll << 30), "stag_spmm: too many work items for one launch");
+  if (q.E > 0) {   // also zeroes the work queue behind the records
     edge_record_kernel<KIND><<<(unsigned)((q.E + 255) / 256), 256, 0, stream>>>(q, const_cast<int4*>(q.rec), 2);
     STAG_LAUNCH_CHECK();
+  } else {
+    STAG_CUDA(cudaMemsetAsync(const_cast<int4*>(q.rec), 0, 16, stream));
   }
   STAG_CUDA(cudaFuncSetAttribute(agg_stream_kernel<KIND, NB, FULL, INNORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
