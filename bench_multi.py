@@ -242,7 +242,7 @@ def minibatch_dp(dev, dist, rank, world, steps, warmup):
 
 # ---- (iii) one large graph, 1-D row partition with halo exchange (C5 products) -------------------------------------
 def row_partition(dev, dist, rank, world, src, dst, N, D, S, steps, warmup, bwd_chunk=8):
-    part = P.RowPartition(src, dst, N, rank, world).setup_halo()
+    part = P.RowPartition(src, dst, N, rank, world, balance="edges").setup_halo()
     lg = part.local_graph(sb.Graph)
     # GCN degree scalings of the UNPARTITIONED graph: sources in extended order (owned rows, then halo rows), owned destinations
     outdeg = torch.bincount(src, minlength=N).clamp_(min=1).to(torch.float32).pow_(-0.5)

@@ -92,6 +92,21 @@ def row_blocks(num_nodes, world):
     return [min(r * per, num_nodes) for r in range(world + 1)], per
 
 
+def edge_balanced_blocks(dst, num_nodes, world):
+    """Block boundaries [world+1] such that every block of destination rows holds about E / world in-edges (the
+    work of the fused pass is per edge; on a power-law graph equal ROW blocks leave the ranks up to 10 % apart, and
+    every exchange then waits for the slowest).  Deterministic: every rank computes the same cuts from `dst`."""
+    deg = torch.bincount(dst, minlength=int(num_nodes))
+    cum = torch.cumsum(deg, 0)
+    E = int(dst.numel())
+    targets = torch.tensor([E * r // world for r in range(1, world)], dtype=cum.dtype, device=cum.device)
+    cuts = (torch.searchsorted(cum, targets, right=False) + 1).clamp_(max=int(num_nodes)).tolist() if world > 1 else []
+    bounds = [0] + [int(c) for c in cuts] + [int(num_nodes)]
+    for i in range(1, len(bounds)):                      # monotone even on degenerate inputs
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds, max(bounds[i + 1] - bounds[i] for i in range(world))
+
+
 def _all_to_all_rows(out, inp, recv_counts, send_counts, group=None, async_op=False):
     """Variable-size row exchange: rows [sum(send_counts[:q]), +send_counts[q]) of `inp` go to rank q, the rows
     received from rank q land at [sum(recv_counts[:q]), +recv_counts[q]) of `out`.  NCCL: one
@@ -139,16 +154,26 @@ class RowPartition:
       are added into the owners' blocks -- the reduce-scatter of dX restricted to the rows that were used.
     * ``halo=False``: all-gather of whole X row blocks / reduce-scatter of a full [N,D] partial dX (round 1).
 
+    ``balance="edges"`` (halo form) cuts the rows so that every rank holds about E / world in-edges instead of N / world
+    rows: the fused pass costs per edge, and every exchange waits for the slowest rank.
+
     Either way the local graph keeps the edge ids of the unpartitioned graph (``eid_map``): the Philox noise of every
     edge, and the order in which a row's in-edges are summed, are those of the single-GPU run -- the forward is
     bitwise identical.  ``aggregate(graph, feat, edge_weight, ...)`` is ``stag_b200.ops.stochastic_aggregate`` on
     the GPU; the CPU tests inject the oracle.
     """
 
-    def __init__(self, src, dst, num_nodes, rank, world, group=None, halo=True):
+    def __init__(self, src, dst, num_nodes, rank, world, group=None, halo=True, balance="rows"):
         self.rank, self.world, self.group = rank, world, group
         self.num_nodes = int(num_nodes)
-        self.bounds, self.per = row_blocks(num_nodes, world)
+        if balance == "edges":
+            if not halo:
+                raise ValueError("balance='edges' needs the halo form (all_gather / reduce_scatter want equal row blocks)")
+            self.bounds, self.per = edge_balanced_blocks(dst, num_nodes, world)
+        elif balance == "rows":
+            self.bounds, self.per = row_blocks(num_nodes, world)
+        else:
+            raise ValueError("balance must be 'rows' or 'edges'")
         self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
         self.n_own = self.hi - self.lo
         own = (dst >= self.lo) & (dst < self.hi)
@@ -160,12 +185,17 @@ class RowPartition:
         if self.halo:
             self._plan_halo()
 
+    def _owner(self, rows):
+        """Owning rank of global rows (int64 tensor)."""
+        cuts = torch.tensor(self.bounds[1:-1], dtype=rows.dtype, device=rows.device)
+        return torch.bucketize(rows, cuts, right=True)
+
     # ---- halo plan ------------------------------------------------------------------------------------------
     def _plan_halo(self):
         src = self.src
         remote = (src < self.lo) | (src >= self.hi)
         self.need = torch.unique(src[remote])            # sorted global ids: grouped by owner, increasing
-        owner = torch.div(self.need, self.per, rounding_mode="floor")
+        owner = self._owner(self.need)
         self.recv_counts = torch.bincount(owner, minlength=self.world).tolist()
         self.n_halo = int(self.need.numel())
         self.n_ext = self.n_own + self.n_halo
@@ -192,7 +222,7 @@ class RowPartition:
             dist.all_to_all_single(sc, rc, group=self.group)
         self.send_counts = sc.tolist()
         owner_lo = torch.tensor(self.bounds[:-1], dtype=torch.int64, device=dev)
-        owner = torch.div(self.need, self.per, rounding_mode="floor")
+        owner = self._owner(self.need)
         req = (self.need - owner_lo[owner]).contiguous()     # row indices inside the owner's block
         self.send_idx = torch.empty(int(sum(self.send_counts)), dtype=torch.int64, device=dev)
         _all_to_all_rows(self.send_idx, req, self.send_counts, self.recv_counts, group=self.group)

@@ -108,3 +108,13 @@ def test_row_partition_keeps_global_noise(arxiv):
         x_ext = torch.cat([x[hp.lo:hp.hi], x[hp.need]])            # what the exchange delivers
         out = sb.ops.stochastic_aggregate(hg, x_ext, sp(hg.number_of_edges()), n_samples=1)[0]
         assert out.shape[0] == hp.n_own and torch.equal(out, full[hp.lo:hp.hi])
+    # edge-balanced cuts (three ranks): every rank about E / 3 in-edges, the blocks still tile the rows, still bitwise
+    sizes = []
+    for rank in range(3):
+        hp = P.RowPartition(ts.cuda(), td.cuda(), N, rank, 3, balance="edges")
+        hg = hp.local_graph(sb.Graph)
+        sizes.append(hg.number_of_edges())
+        x_ext = torch.cat([x[hp.lo:hp.hi], x[hp.need]])
+        out = sb.ops.stochastic_aggregate(hg, x_ext, sp(hg.number_of_edges()), n_samples=1)[0]
+        assert torch.equal(out, full[hp.lo:hp.hi])
+    assert sum(sizes) == E and max(sizes) - min(sizes) < 0.01 * E

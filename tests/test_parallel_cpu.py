@@ -84,6 +84,14 @@ def _worker(rank, world, port, ret):
         out_h.backward(G[hp.lo:hp.hi])
         dx_h = hp.exchange_back(x_ext.grad)
         assert torch.allclose(dx_h, Xo.grad[hp.lo:hp.hi], atol=1e-5)
+        # --- the same with edge-balanced cuts: rows split so that the ranks hold about E / world in-edges each --------
+        he = P.RowPartition(src, dst, N, rank, world, balance="edges").setup_halo()
+        assert he.bounds[0] == 0 and he.bounds[-1] == N and abs(int(he.src.numel()) - src.numel() // world) <= int(torch.bincount(dst).max())
+        xe = he.exchange(X[he.lo:he.hi].contiguous()).requires_grad_(True)
+        out_e = ref_spmm.aggregate(he.src_ext, he.dst_loc, he.n_ext, xe, W[he.edge_ids])[: he.n_own]
+        assert torch.equal(out_e.detach(), full.detach()[he.lo:he.hi])
+        out_e.backward(G[he.lo:he.hi])
+        assert torch.allclose(he.exchange_back(xe.grad), Xo.grad[he.lo:he.hi], atol=1e-5)
         # sample-batched exchange [S, rows, D]
         X3 = torch.stack([X, 2 * X])
         x3 = hp.exchange(X3[:, hp.lo:hp.hi].contiguous())
@@ -99,6 +107,26 @@ def test_world_size_2_gloo():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_edge_balanced_blocks_single_process():
+    import pytest
+    from stag_b200 import parallel as P
+    g = torch.Generator().manual_seed(3)
+    N, E = 1000, 20000
+    dst = (torch.rand(E, generator=g) ** 3 * N).long().clamp_(max=N - 1)      # skewed in-degrees
+    for world in (1, 2, 3, 8):
+        bounds, per = P.edge_balanced_blocks(dst, N, world)
+        assert bounds[0] == 0 and bounds[-1] == N and all(b1 >= b0 for b0, b1 in zip(bounds, bounds[1:])) and len(bounds) == world + 1
+        cnt = [int(((dst >= bounds[r]) & (dst < bounds[r + 1])).sum()) for r in range(world)]
+        assert sum(cnt) == E and max(cnt) - E // world <= int(torch.bincount(dst).max())
+        assert per == max(b1 - b0 for b0, b1 in zip(bounds, bounds[1:]))
+    part = P.RowPartition(torch.zeros(E, dtype=torch.long), dst, N, 1, 3, balance="edges")
+    rows = torch.arange(N)
+    own = part._owner(rows)
+    assert all(int(own[b]) == r for r, b in enumerate(part.bounds[:-1]) if part.bounds[r + 1] > b)
+    with pytest.raises(ValueError):
+        P.RowPartition(torch.zeros(E, dtype=torch.long), dst, N, 0, 2, halo=False, balance="edges")
 
 
 def test_row_blocks_and_sample_shards_single_process():

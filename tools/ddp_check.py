@@ -86,7 +86,7 @@ def main():
     err_dx = rel(dx_block, Xr.grad[part.lo:part.hi])
 
     # ---- 4: row partition with a proper halo (only the referenced source rows travel; bipartite local graph) ----
-    hp = P.RowPartition(ts.cuda(), td.cuda(), N, rank, world).setup_halo()
+    hp = P.RowPartition(ts.cuda(), td.cuda(), N, rank, world, balance="edges").setup_halo()
     hg = hp.local_graph(stag.Graph)
     x_ext = hp.exchange(X[hp.lo:hp.hi].contiguous()).requires_grad_(True)
     S = 3
