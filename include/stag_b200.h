@@ -169,6 +169,11 @@ STAG_API int stag_csx_build(const int64_t* src, const int64_t* dst, int64_t num_
  *
  * The same entry point run on the CSR graph with (src_scale, dst_scale) swapped and
  * x := dOut is the transposed aggregation, i.e. dX of the backward pass.
+ *
+ * The workspace holds per-call state (edge records, hub partial sums, the work-queue counter of the streaming
+ * kernels): calls that may run concurrently (different streams) need a workspace each.  Results do not depend on
+ * how the queue hands the work out (every output row is summed by one thread group in stored-edge order): bitwise
+ * run-to-run.
  */
 STAG_API size_t stag_spmm_workspace_bytes(const StagGraph* g, int32_t D, int32_t S);
 STAG_API int stag_spmm_fwd(const StagGraph* g, const float* x, int64_t ldx, int64_t x_sample_stride,
