@@ -161,7 +161,8 @@ def hadamard_sums(num_edges, K, sample, seed, offset):
     """float64 [E, K] raw sums (exact: multiples of 2^-8 below 2^12), original edge order."""
     assert K % 128 == 0
     G = K // 128
-    eid = np.arange(num_edges, dtype=np.uint32)[:, None]
+    eid = _edge_ids(num_edges)[:, None]        # a count, or an array of edge ids
+    num_edges = eid.shape[0]
     blk = np.arange(8 * G, dtype=np.uint32)[None, :]
     r = np.stack(raw_block(eid, blk, np.uint32(sample), seed, offset), axis=-1)          # [E, 8G, 4] words
     by = np.stack([(r >> np.uint32(8 * b)) & np.uint32(0xFF) for b in range(4)], axis=-1)  # [E, 8G, 4, 4]

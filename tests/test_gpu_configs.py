@@ -185,6 +185,7 @@ def test_c5_products_shaped_properties():
     # CSC, the noise of exactly those edges from the numpy restatement of the generator (oracle/ref_philox.py), the
     # reference's sum in edge-id order in float64 (stag/zoo/gcn.py:63,94-96 with fn.mean)
     from oracle import ref_philox
+    from stag_b200 import _lib
     full = sb.ops.stochastic_aggregate(g, x.detach(), spec(E), reduce="mean", n_samples=1)[0]
     rows = torch.from_numpy(np.random.default_rng(1).choice(N, 3000, replace=False)).cuda()
 
@@ -193,7 +194,10 @@ def test_c5_products_shaped_properties():
         cnt = (b - a).cpu().numpy()
         pos = torch.cat([torch.arange(int(lo_), int(hi_), device="cuda") for lo_, hi_ in zip(a.tolist(), b.tolist())])
         ids, nbr = eid.long()[pos].cpu().numpy(), indices.long()[pos]
-        w = ref_philox.noise("normal", ids, D, 0, 3, 9, 1.0, 0.4).astype(np.float64)
+        if spec(E).lib_kind == _lib.NOISE_NORMAL_HADAMARD:   # D = 100 runs padded to one 128-channel group on the tensor cores
+            w = ref_philox.noise("normal_hadamard", ids, spec(E).hadamard_width, 0, 3, 9, 1.0, 0.4)[:, :D].astype(np.float64)
+        else:
+            w = ref_philox.noise("normal", ids, D, 0, 3, 9, 1.0, 0.4).astype(np.float64)
         msg = w * operand[nbr].double().cpu().numpy()
         seg = np.repeat(np.arange(len(cnt)), cnt)
         exp = np.zeros((len(cnt), D))

@@ -36,6 +36,24 @@ def test_emit_is_bit_exact_against_numpy(K):
     np.testing.assert_allclose(w, ref_philox.noise("normal_hadamard", E, K, 0, 1, 2, loc_e, scale_e), rtol=0, atol=2e-7)
 
 
+@pytest.mark.parametrize("K", [100, 97, 250])
+def test_widths_within_a_third_of_a_group_run_padded(K):
+    """K = 100 (products) runs at 128: the emitted stream is the first K columns of the 128-wide one, and 'auto' picks
+    the tensor-core generator there."""
+    from stag_b200 import _lib
+    from stag_b200.ops import NoiseSpec
+    E, Kp = 1 << 18, (K + 127) // 128 * 128
+    assert spec(1.0, 0.5, K, E - 1).hadamard_width == 0          # short passes do not pay for the pad / slice launches
+    sp = spec(1.0, 0.5, K, E, seed=5, offset=6)
+    assert sp.hadamard_width == Kp and sp.lib_kind == _lib.NOISE_NORMAL_HADAMARD
+    one = torch.ones((), device="cuda")
+    assert NoiseSpec("normal", one, one, K, E).lib_kind == _lib.NOISE_NORMAL_HADAMARD          # generator=None -> auto
+    assert NoiseSpec("normal", one, one, K, E, generator="boxmuller").lib_kind == _lib.NOISE_NORMAL
+    w = sp.materialize(n_samples=2)[:, :4097].cpu().numpy()
+    for s in range(2):
+        assert np.array_equal(w[s], ref_philox.noise("normal_hadamard", 4097, Kp, s, 5, 6, 1.0, 0.5)[:, :K])
+
+
 def test_tensor_core_sums_equal_the_emitted_stream_bitwise():
     """One in-edge per node, x = 1, loc = 0, scale = 1, no degree scales: out[v] is the noise row of v's edge."""
     import stag_b200 as sb
@@ -79,7 +97,8 @@ def test_moments_ks_independence():
 
 @pytest.mark.parametrize("N,E,D,S,shared,hub", [
     (500, 3000, 128, 3, True, 0), (500, 3000, 128, 3, False, 0), (3000, 40000, 256, 2, False, 9000),
-    (300, 100, 128, 1, True, 0), (700, 9000, 384, 2, True, 2500), (5000, 70001, 128, 5, False, 300)])
+    (300, 100, 128, 1, True, 0), (700, 9000, 384, 2, True, 2500), (5000, 70001, 128, 5, False, 300),
+    (5000, 1 << 18, 100, 2, True, 0), (8000, 300000, 200, 1, False, 300)])   # padded to the next group (graphs of >= 2^18 edges)
 def test_fused_forward_and_transposed_pass_consume_the_emitted_noise(N, E, D, S, shared, hub):
     import stag_b200 as sb
     rng = np.random.default_rng(N + E)
@@ -128,7 +147,7 @@ def test_unsupported_combinations_are_refused():
     from stag_b200 import _lib
     from stag_b200.ops import NoiseSpec
     one = torch.ones((), device="cuda")
-    for kw in (dict(K=100), dict(K=128, relu=True), dict(K=128, in_norm=True)):
+    for kw in (dict(K=64), dict(K=130), dict(K=128, relu=True), dict(K=128, in_norm=True)):
         K = kw.pop("K")
         with pytest.raises(ValueError):
             NoiseSpec("normal", one, one, K, 10, generator="hadamard", **kw).lib_kind
