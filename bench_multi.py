@@ -74,6 +74,11 @@ class AggStack:
         self.csr, self._k2 = st.csx(False)
         self.n_dst, self.n_src, self.E = st.num_nodes, st.num_src, st.num_edges
         self.ss, self.ds = src_scale, dst_scale
+        self.logical = list(widths)
+        # what stag_b200.ops.stochastic_aggregate does with generator "auto": a width within a third of a multiple of 128
+        # runs zero-padded on the tensor-core generator (products' 100 -> 128)
+        pad = lambda D: (D + 127) // 128 * 128 if (normal == "hadamard" and D >= 96 and D % 128 and 3 * ((D + 127) // 128 * 128) <= 4 * D) else D  # noqa: E731
+        widths = [pad(D) for D in widths]
         self.widths = list(widths)
         gen = torch.Generator(device=dev).manual_seed(4321)
         self.x = [torch.randn((self.n_src, widths[0]), device=dev, generator=gen)]                   # layer-1 input: shared
@@ -84,7 +89,13 @@ class AggStack:
         # over the samples: chunks bound its size)
         self.chunk = S if bwd_chunk is None else max(1, min(S, bwd_chunk))
         self.dx = [torch.empty((self.chunk, self.n_src, D), device=dev) for D in widths]
-        self.dx_sum = torch.zeros((self.n_src, widths[0]), device=dev)
+        self._dx_sum = torch.zeros((self.n_src, widths[0]), device=dev)
+        self.dx_sum = self._dx_sum[:, : self.logical[0]]            # the caller's view: logical width
+        for k, (Dl, Dk) in enumerate(zip(self.logical, widths)):    # padded channels carry zeros
+            if Dk != Dl:
+                self.x[k][..., Dl:] = 0
+                self.gout[k][..., Dl:] = 0
+        self._xin = None
         self.loc = torch.ones(1, device=dev)
         self.scale = torch.full((1,), 0.4, device=dev)
         self.normal = normal
@@ -109,6 +120,11 @@ class AggStack:
     def fwd(self, layer, x=None):
         D = self.widths[layer]
         x = self.x[layer] if x is None else x
+        if x.shape[-1] != D:             # operand handed in at its logical width: into a zero-padded buffer (the operator's pad)
+            if self._xin is None or self._xin.shape[:-1] != x.shape[:-1]:
+                self._xin = torch.zeros(tuple(x.shape[:-1]) + (D,), device=self.dev)
+            self._xin[..., : x.shape[-1]].copy_(x)
+            x = self._xin
         shared = x.dim() == 2
         nz = self._noise(layer, D, self.sample_base)
         _lib.check(self.lib.stag_spmm_fwd(
@@ -128,9 +144,9 @@ class AggStack:
                 self.ws.data_ptr(), self.ws.numel(), self.stream))
             if layer == 0:   # shared operand: its gradient is the sum over the samples
                 if s0 == 0:
-                    torch.sum(self.dx[0][:ns], 0, out=self.dx_sum)
+                    torch.sum(self.dx[0][:ns], 0, out=self._dx_sum)
                 else:
-                    self.dx_sum += self.dx[0][:ns].sum(0)
+                    self._dx_sum += self.dx[0][:ns].sum(0)
 
     def forward_all(self):
         for layer in range(len(self.widths)):
@@ -250,7 +266,7 @@ def row_partition(dev, dist, rank, world, src, dst, N, D, S, steps, warmup, bwd_
     ext_ids = torch.cat([torch.arange(part.lo, part.hi, device=dev), part.need])
     ss_ext, ds_own = outdeg[ext_ids].contiguous(), indeg[part.lo:part.hi].contiguous()
     del outdeg, indeg
-    stack = AggStack(dev, lg, [D], S, 0, ss_ext, ds_own, normal="boxmuller", bwd_chunk=bwd_chunk)
+    stack = AggStack(dev, lg, [D], S, 0, ss_ext, ds_own, normal="hadamard", bwd_chunk=bwd_chunk)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     x_block = torch.randn(part.n_own, D, device=dev, generator=gen)
     x_ext = torch.empty(part.n_ext, D, device=dev)
@@ -289,7 +305,8 @@ def row_partition(dev, dist, rank, world, src, dst, N, D, S, steps, warmup, bwd_
     dist.all_reduce(sizes, op=dist.ReduceOp.MAX)
     E = int(src.numel())
     return {"workload": "C5 products-shaped graph (N=%d, E=%d, D=%d), ONE graph row-partitioned over %d GPUs, 1 stag GCN "
-                        "aggregation forward + transposed pass over %d MC samples (shared X)" % (N, E, D, world, S),
+                        "aggregation forward + transposed pass over %d MC samples (shared X); D = 100 runs zero-padded at 128 on the tensor-core "
+                        "generator, as the public operator does" % (N, E, D, world, S),
             "scaling": "strong", "ms_per_step": t_step, "compute_ms": fwd_ms + bwd_ms, "collective_ms": halo_ms + back_ms,
             "exposed_ms": halo_ms + back_ms, "exposed_frac_of_step": (halo_ms + back_ms) / max(t_step, 1e-9),
             "halo_exchange_ms": halo_ms, "forward_ms": fwd_ms, "transposed_ms": bwd_ms, "gradient_return_ms": back_ms,
@@ -324,8 +341,9 @@ def run_all(dev, dist, rank, world, steps, warmup, normal):
     torch.cuda.empty_cache()
     out["c5_products_strong_mc"] = strong_mc(
         dev, dist, rank, world, "C5 products-shaped graph (N=%d, E=%d, D=%d), graph replicated, the 32 MC samples split over "
-        "the GPUs, 1 aggregation forward + transposed pass" % (N5, E5, D5), s5, d5, N5, [D5], S5, 47, max(3, steps // 2), 3,
-        "boxmuller", bwd_chunk=8)
+        "the GPUs, 1 aggregation forward + transposed pass; D = 100 runs zero-padded at 128 on the tensor-core generator" % (N5, E5, D5),
+        s5, d5, N5, [D5], S5, 47, max(3, steps // 2), 3,
+        "hadamard", bwd_chunk=8)
     out["seconds"] = time.perf_counter() - t0
     return out
 
