@@ -20,8 +20,8 @@ import torch
 from . import _lib, random as _random
 from .graph import as_graph
 
-# 'auto' = the tensor-core generator wherever the fused kernel takes it (K % 128 == 0, scalar / per-edge parameters
-# without gradients, no relu / in-norm: 1.49 ms per arxiv launch against 1.68), else Box-Muller
+# 'auto' = the tensor-core generator wherever the fused kernel takes it (K % 128 == 0 or padded to it: NoiseSpec.hadamard_width; scalar / per-edge parameters
+# without gradients, no relu / in-norm: 1.35 ms per arxiv launch against 1.56), else Box-Muller
 _DEFAULT_NORMAL_GENERATOR = "auto"
 _KIND = {"normal": _lib.NOISE_NORMAL, "uniform": _lib.NOISE_UNIFORM, "bernoulli": _lib.NOISE_BERNOULLI}
 
@@ -55,7 +55,8 @@ class NoiseSpec:
     generator        how standard normals are drawn: 'boxmuller' (16-bit Box-Muller in the CUDA cores),
                      'hadamard' (Walsh-Hadamard mix of random FP8 bytes on the tensor cores,
                      csrc/spmm_tc.cuh, spmm_wq.cuh) or None = hadamard wherever the fused kernel takes it (K a
-                     multiple of 128, scalar or per-edge parameters without gradients, no relu / in-norm),
+                     multiple of 128 -- or within a third of one on graphs of >= 2^18 edges, run zero-padded:
+                     ``hadamard_width`` -- scalar or per-edge parameters without gradients, no relu / in-norm),
                      else boxmuller; env STAG_NORMAL_GENERATOR (boxmuller | hadamard | auto) overrides the None case.  The forward, the transposed pass and
                      ``materialize`` of one spec always use the same generator.
     """
