@@ -6,16 +6,22 @@
 // GCN.forward (stag/zoo/gcn.py:97-114) and the fc_neigh / fc_self Linear layers of GraphSAGE
 // (stag/zoo/graph_sage.py:74-75,91,107).
 //
-// One CTA (4 warps) owns a 128-row tile of A and ALL output columns (N <= 256):
-//   per K block of 32 floats:  threads load the A tile and the W^T tile with 128-bit loads, split
+// Two kernels:
+//   gemm_tma_kernel      persistent, one CTA of 10 warps per SM, W_hi / W_lo of every K block resident in shared memory,
+//                        A tiles by TMA into a ring, split / MMA / epilogue in separate warps, two TMEM accumulators
+//                        (taken when rows of A are 16-byte aligned and W fits: the layer shapes; see further down);
+//   gemm_tcgen05_kernel  the first form, below: one CTA (4 warps) owns a 128-row tile of A and ALL output columns
+//                        (N <= 256); with few row tiles and a long K (Cora: 2 708 x 1 433 x 16) the K blocks of one row
+//                        tile are split over a thread-block cluster and added in rank 0's shared memory (DSMEM).
+// First form, per K block of 32 floats:  threads load the A tile and the W^T tile with 128-bit loads, split
 //   them into hi / lo parts and store them into shared memory in the canonical K-major
 //   SWIZZLE_128B layout (rows of 128 bytes, 16-byte chunks XOR-ed with row % 8);  one elected
 //   thread issues 4 k-steps x 3 tcgen05.mma (kind::tf32, M = 128, N = Npad, K = 8) accumulating
 //   into TMEM;  tcgen05.commit -> mbarrier releases the shared tiles.
 //   epilogue: each warp reads its 32 TMEM lanes (tcgen05.ld 32x32b.x32), applies row scale, bias,
 //   activation and writes 128-byte row segments.
-// Two CTAs are resident per SM (96 KB of shared memory each), which overlaps one CTA's loads with
-// the other's MMAs; the kernel is bound by the A read / out write stream, not by the tensor pipe.
+// Two CTAs of the first form are resident per SM (96 KB of shared memory each), which overlaps one CTA's loads with
+// the other's MMAs.  Timings and the ncu reading: profiles/r02_gemm.txt.
 #include <cuda.h>  // CUtensorMap: types only, the encoder comes from cudaGetDriverEntryPoint
 #include <stdlib.h>
 
@@ -320,18 +326,21 @@ __global__ void __launch_bounds__(GTHREADS) gemm_tcgen05_kernel(const GemmParams
 // ---- second form: persistent CTAs, W resident in shared memory, A tiles by TMA ------------------------------------
 // For the memory-bound layer shapes (arxiv: M = S N = 2.7 M rows, K = N = 128: 1.39 GB in, 1.39 GB out, 0.09 TFLOP) the
 // first form re-splits the W tile for every row tile and K block and moves A through registers with one K block in
-// flight.  Here a CTA per SM keeps W_hi / W_lo of ALL K blocks in shared memory (swizzled once), and a 3-stage ring of
-// [128 x 32] fp32 A tiles is filled by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B: the tile lands in the canonical
-// K-major layout the MMA reads) -- roles:
-//   warp 0   one thread: waits for a free stage, arms its mbarrier with the tile's bytes, issues the TMA load;
-//   warps 2-5  when a tile has landed: split it IN PLACE into hi (low 13 mantissa bits cleared: exactly what a tf32
-//            operand keeps) and lo = tf32(x - hi) (second buffer of the stage), fence.proxy.async, arrive on `ready`;
-//   warps 6-9  epilogue of a finished row tile from its TMEM accumulator (32x32b loads, row scale, bias, relu, row
-//            stores), arrive on `acc_empty` -- while the other accumulator is being filled (with the split warps doing
-//            the epilogue too, the pipeline drained during every epilogue: 1.75 ms instead of 1.47 for the first form);
+// flight.  Here a CTA per SM keeps W_hi / W_lo of ALL K blocks in shared memory (swizzled once), and a ring of
+// [128 x 32] fp32 A tiles (sized at run time: what fits beside W, 3 at K = N = 128) is filled by TMA
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B: the tile lands in the canonical K-major layout the MMA reads) -- roles:
+//   warp 0   one thread: waits for a free ring slot, arms its mbarrier with the tile's bytes, issues the TMA load;
+//   warps 2-5  when a tile has landed: kind::tf32 reads the upper 19 bits of a 32-bit container, so the tile as delivered
+//            IS the hi operand; these warps only make lo = tf32(x - trunc(x)) into a second ring (2-3 tiles),
+//            fence.proxy.async, arrive on `ready`;
 //   warp 1   one thread: waits for `ready`, issues 4 k-steps x 3 tcgen05.mma (A_hi W_hi + A_lo W_hi + A_hi W_lo) into
-//            TMEM accumulator [tile & 1], tcgen05.commit -> `empty` (stage reusable) and, after the last K block, ->
-//            `acc_full`.
+//            TMEM accumulator [tile & 1]; tcgen05.commit -> `empty` (raw slot reusable) and `lo_free`, and after the
+//            last K block of a row tile -> `acc_full`;
+//   warps 6-9  epilogue of a finished row tile from its TMEM accumulator while the other one is being filled: 32x32b
+//            loads (the next 32 columns in flight), row scale, XOR-swizzled scratch, bias, relu, STG.128 of four
+//            128-byte row segments per instruction; `acc_empty` right after the last TMEM read.
+// (With the split warps also running the epilogue the pipeline drained during every epilogue: 1.75 ms; with a thread
+// storing its own row: 1.48 ms; now 0.56 - 0.60 ms, profiles/r02_gemm.txt.)
 // Out-of-range rows / columns of A are zero-filled by the TMA unit (the tensor map knows M and K).
 constexpr int G2_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
 constexpr int G2_MAXST = 8;      // ring sizes are run-time (what fits beside the resident W): at most 8 raw / 8 lo tiles
