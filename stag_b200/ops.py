@@ -58,7 +58,9 @@ class NoiseSpec:
                      multiple of 128 -- or within a third of one on graphs of >= 2^18 edges, run zero-padded:
                      ``hadamard_width`` -- scalar or per-edge parameters without gradients, no relu / in-norm),
                      else boxmuller; env STAG_NORMAL_GENERATOR (boxmuller | hadamard | auto) overrides the None case.  The forward, the transposed pass and
-                     ``materialize`` of one spec always use the same generator.
+                     ``materialize`` of one spec always use the same generator.  (The tensor-core kernel addresses the
+                     gathered operand with 32-bit byte offsets: beyond 4 GB per sample -- 8.4 M nodes at 128 channels --
+                     it is refused with STAG_EUNSUPPORTED; pass generator='boxmuller' there.)
     """
 
     def __init__(self, kind, p0, p1, K, num_edges, relu=False, in_norm=False, seed=None, offset=None,
