@@ -226,3 +226,33 @@ def test_model_api_carries_sample_base_and_layers_pickle():
     assert sb.zoo.GCN.accepts_sample_batch and not sb.zoo.GatedGCN.accepts_sample_batch
     m = sb.models.StagModel(torch.nn.ModuleList([sb.layers.StagLayer(sb.zoo.GatedGCN(4, 4))]))
     assert m._can_batch() is False
+
+
+def test_generator_selection_rules_of_a_noise_spec():
+    """Which standard-normal generator a NoiseSpec resolves to (no device needed): the tensor-core one where the fused
+    kernel takes it -- K a multiple of 128, or K >= 96 within a third of one on graphs of >= 2^18 edges (run
+    zero-padded) -- with scalar / per-edge parameters without gradients and no relu / in-norm; Box-Muller otherwise;
+    an explicit 'hadamard' outside that set is refused, never re-routed."""
+    import pytest
+    import torch
+    from stag_b200 import _lib
+    from stag_b200.ops import NoiseSpec
+    one = torch.ones(())
+    big = 1 << 18
+    for K, E, width in [(128, 10, 128), (384, 10, 384), (100, big, 128), (100, big - 1, 0), (97, big, 128), (95, big, 0),
+                        (130, big, 0), (200, big, 256), (1433, big, 1536), (64, big, 0), (1, big, 0)]:
+        sp = NoiseSpec("normal", one, one, K, E)
+        assert sp.hadamard_width == width, (K, E)
+        assert sp.lib_kind == (_lib.NOISE_NORMAL_HADAMARD if width else _lib.NOISE_NORMAL)
+        assert NoiseSpec("normal", one, one, K, E, generator="boxmuller").lib_kind == _lib.NOISE_NORMAL
+        # every view of a spec agrees (the emitted tensor and the fused passes must draw the same stream)
+        assert sp.with_samples(1).lib_kind == sp.with_samples(16, 3).lib_kind == sp.lib_kind
+    for kw in (dict(relu=True), dict(in_norm=True)):
+        assert NoiseSpec("normal", one, one, 128, 10, **kw).lib_kind == _lib.NOISE_NORMAL
+        with pytest.raises(ValueError):
+            NoiseSpec("normal", one, one, 128, 10, generator="hadamard", **kw).lib_kind
+    learn = torch.ones(128, requires_grad=True)
+    assert NoiseSpec("normal", learn, torch.ones(128), 128, 10).lib_kind == _lib.NOISE_NORMAL     # vi: two-sum kernel
+    assert NoiseSpec("uniform", one, 2 * one, 128, 10).lib_kind == _lib.NOISE_UNIFORM
+    with pytest.raises(ValueError):
+        NoiseSpec("normal", one, one, 128, 10, generator="ziggurat")
