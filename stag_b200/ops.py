@@ -478,6 +478,73 @@ def stochastic_aggregate(graph, feat, edge_weight=None, reduce="sum", src_scale=
     return out[0] if squeeze else out
 
 
+class _HeadsAggregate(torch.autograd.Function):
+    """out[v, k, :] = sum over the in-edges e = (u, v) of a[e, k] * ft[u, k, :]  -- the weighted aggregation of a
+    multi-head attention layer (GATConv's ``u_mul_e('ft', 'a') -> sum``).  One launch per head on the per-edge-weight
+    kernel, each reading its F columns of ``ft`` IN PLACE (row stride H F) and writing its F columns of ``out`` in
+    place: no ``[E, H F]`` expansion of the attention, no per-head copies.  Backward: per head the transposed pass
+    (d ft) and the SDDMM (d a) in one ``stag_spmm_bwd`` call."""
+
+    @staticmethod
+    def forward(ctx, ft, a, graph):
+        st = graph._s
+        dev = ft.device
+        _require_cuda(ft, "feat")
+        lib = _lib.load()
+        N, NS, E = st.num_nodes, st.num_src, st.num_edges
+        H, F = ft.shape[-2], ft.shape[-1]
+        x = _c(ft.to(torch.float32)).reshape(NS, H * F)
+        at = a.detach().to(torch.float32).t().contiguous()               # [H, E]: the weights of a head are one row
+        out = torch.empty((N, H * F), dtype=torch.float32, device=dev)
+        with _on_device(dev):
+            csc, _ = st.csx(True)
+            ws = _workspace(st, lib, csc, True, F, 1)
+            for k in range(H):
+                nz = _fill_noise(None, _lib.NOISE_EXTERNAL, 1, None, None, at[k], False, False, 0, 0, 0, _lib.PARAM_SCALAR)
+                _lib.check(lib.stag_spmm_fwd(
+                    ctypes.byref(csc), x.data_ptr() + 4 * k * F, H * F, 0, F, 1, ctypes.byref(nz), 0, 0,
+                    out.data_ptr() + 4 * k * F, H * F, N * H * F, 0, ws.data_ptr(), ws.numel(), _stream(dev)))
+        ctx.graph, ctx.dims = graph, (N, NS, E, H, F)
+        ctx.save_for_backward(x, at)
+        return out.reshape(N, H, F)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, at = ctx.saved_tensors
+        N, NS, E, H, F = ctx.dims
+        st = ctx.graph._s
+        lib = _lib.load()
+        dev = gout.device
+        g2 = gout.to(torch.float32).contiguous().reshape(N, H * F)
+        need_dx, need_da = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx = torch.empty((NS, H * F), dtype=torch.float32, device=dev) if need_dx else None
+        dat = torch.empty((H, E), dtype=torch.float32, device=dev) if need_da else None
+        with _on_device(dev):
+            csr, _ = st.csx(False)
+            ws = _workspace(st, lib, csr, False, F, 1)
+            for k in range(H):
+                nz = _fill_noise(None, _lib.NOISE_EXTERNAL, 1, None, None, at[k], False, False, 0, 0, 0, _lib.PARAM_SCALAR)
+                if need_da:
+                    _lib.check(lib.stag_spmm_bwd(
+                        ctypes.byref(csr), x.data_ptr() + 4 * k * F, H * F, 0, g2.data_ptr() + 4 * k * F, H * F, N * H * F,
+                        F, 1, ctypes.byref(nz), 0, 0, 0 if dx is None else dx.data_ptr() + 4 * k * F, H * F, NS * H * F,
+                        0, 0, dat[k].data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)))
+                elif need_dx:
+                    _lib.check(lib.stag_spmm_fwd(
+                        ctypes.byref(csr), g2.data_ptr() + 4 * k * F, H * F, 0, F, 1, ctypes.byref(nz), 0, 0,
+                        dx.data_ptr() + 4 * k * F, H * F, NS * H * F, 0, ws.data_ptr(), ws.numel(), _stream(dev)))
+        return (None if dx is None else dx.reshape(NS, H, F)), (None if dat is None else dat.t()), None
+
+
+def heads_aggregate(graph, ft, a):
+    """Per-head weighted aggregation ``[N_src, H, F], [E, H] -> [N, H, F]`` (see :class:`_HeadsAggregate`)."""
+    g = as_graph(graph)
+    if ft.dim() != 3 or a.dim() != 2 or a.shape[1] != ft.shape[1] or a.shape[0] != g.number_of_edges():
+        raise ValueError("heads_aggregate: feat [N,H,F] and attention [E,H] expected, got %s and %s"
+                         % (tuple(ft.shape), tuple(a.shape)))
+    return _HeadsAggregate.apply(ft, a, g)
+
+
 def segment_reduce(graph, feat, mean=False):
     """SumNodes / MeanNodes readout (stag/layers.py:156-178): [N,D] -> [B,D] by batch_num_nodes."""
     return _SegmentReduce.apply(feat, as_graph(graph), bool(mean))

@@ -2,8 +2,8 @@
 The noise ``[E,H]`` multiplies the pre-softmax logits (:117-119).  The segmented softmax over the in-edges of each
 node runs on ``stag_edge_softmax`` (forward and backward in one fused pass each, csrc/edge_softmax.cu) and the final
 weighted aggregation ``update_all(u_mul_e('ft','a'), sum)`` (:125-126) on ``stag_spmm_fwd`` with the attention as
-external weights (all heads in one launch while the expanded ``[E, H*F]`` weights stay below 256 MB, else one
-launch per head).  The logits and the noise product are elementwise torch ops on ``[E,H]``.
+external weights: all heads in one launch with expanded ``[E, H*F]`` weights on small (launch-bound) graphs (<= 4 MB),
+else ``ops.heads_aggregate`` -- one launch per head, every head reading / writing its F columns in place.  The logits and the noise product are elementwise torch ops on ``[E,H]``.
 ``accepts_noise_spec`` is False: the noise multiplies the LOGITS, not the messages, so ``StagLayer`` hands this
 layer a tensor emitted from the library's Philox stream (``stag_noise_emit``, K = num_heads).
 """
@@ -69,16 +69,16 @@ class GAT(nn.Module):
             e = edge_weight * e
         # segmented softmax over the in-edges of each node: one fused pass (stag_edge_softmax)
         a = self.attn_drop(ops.edge_softmax(g, e))                 # [E,H]
-        if a.shape[0] * H * F * 4 <= (256 << 20):
-            # weighted aggregation on the fused kernel in ONE launch over the H*F channels: the attention of head k is the
-            # weight of channels k*F .. (k+1)*F - 1 (external per-channel weights [E, H*F]; autograd sums the SDDMM
-            # gradient back over the F channels of a head)
+        if a.shape[0] * H * F * 4 <= (4 << 20):
+            # small graphs are launch-bound: ONE fused launch over the H*F channels, the attention of head k expanded to the
+            # weight of channels k*F .. (k+1)*F - 1 (external per-channel weights [E, H*F], at most 4 MB; autograd sums the
+            # SDDMM gradient back over the F channels of a head)
             aw = a.unsqueeze(-1).expand(a.shape[0], H, F).reshape(a.shape[0], H * F)
             rst = ops.stochastic_aggregate(g, ft.reshape(N, H * F), aw).view(N, H, F)
         else:
-            # large graphs: the expanded weights would be E*H*F floats; one launch per head with [E,1] weights instead
-            outs = [ops.stochastic_aggregate(g, ft[:, k, :].contiguous(), a[:, k:k + 1].contiguous()) for k in range(H)]
-            rst = torch.stack(outs, dim=1)                         # [N,H,F]
+            # one launch per head on the per-edge-weight kernel, every head reading / writing its F columns in place (row
+            # stride H*F): no [E, H*F] expansion, no per-head copies
+            rst = ops.heads_aggregate(g, ft, a)
         if self.res_fc is not None:
             rst = rst + self.res_fc(h).view(N, -1, F)
         if self.bias is not None:
