@@ -141,3 +141,14 @@ def test_hadamard_generator_restatement_law():
     assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2.0 / n)
     assert abs(stats.kurtosis(z.ravel())) < 5 * np.sqrt(24.0 / n)
     assert stats.kstest(z.ravel(), "norm").pvalue > 1e-3
+
+
+def test_generators_accept_edge_id_subsets():
+    """`num_edges` may be an array of edge ids (row subsets of graphs too large to materialise [E,K] for: the
+    products-shape parity test): the variates of exactly those edges, for every distribution kind."""
+    from oracle import ref_philox
+    ids = np.array([7, 3, 49, 3, 0], dtype=np.int64)
+    for kind, K, p0, p1 in [("normal", 40, 1.0, 0.4), ("normal_hadamard", 256, 1.0, 0.4), ("uniform", 24, 0.3, 1.7),
+                            ("bernoulli", 16, 0.8, None)]:
+        full = ref_philox.noise(kind, 50, K, 2, 11, 3, p0, p1)
+        assert np.array_equal(ref_philox.noise(kind, ids, K, 2, 11, 3, p0, p1), full[ids]), kind
