@@ -245,6 +245,17 @@ STAG_API int stag_edge_softmax(const StagGraph* csc, const float* logits, int32_
 STAG_API int stag_edge_softmax_bwd(const StagGraph* csc, const float* a, const float* da, int32_t H, float* dlogits,
                           void* stream);
 
+/* The same with GAT's attention logits computed inside (stag/zoo/gat.py:113-122):
+ *   logit[e,h] = w[e,h] * leaky_relu(el[u_e,h] + er[v_e,h], slope),   a[e,h] = softmax over the in-edges of v_e
+ * el [num_cols,H] (source rows), er [num_rows,H], w [E,H] in original edge order or NULL (no edge noise); a [E,H].
+ * Backward from da [E,H]: dw [E,H] (may be NULL), dpre [E,H] = d(el[u] + er[v]) per edge (the caller sums it per SOURCE
+ * on the CSR graph: d el), d_er [num_rows,H] = its sum per destination.  No atomics: deterministic. */
+STAG_API int stag_attention_softmax(const StagGraph* csc, const float* el, const float* er, const float* w, float slope,
+                           int32_t H, float* a, void* stream);
+STAG_API int stag_attention_softmax_bwd(const StagGraph* csc, const float* el, const float* er, const float* w, float slope,
+                               int32_t H, const float* a, const float* da, float* dw, float* dpre, float* d_er,
+                               void* stream);
+
 /* Likelihood epilogue (stag/models.py:69-72, stag/likelihoods.py:13-38): for each of the S Monte-Carlo outputs
  *   nll_out[s] = mean over the masked nodes of -log_prob(probs[s], y)
  * kind 0: Categorical(probs=.) -- probs renormalised, clamped to [eps, 1-eps], log, gathered at y (int64 [N]);

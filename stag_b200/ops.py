@@ -608,6 +608,80 @@ class _EdgeSoftmax(torch.autograd.Function):
         return dl, None
 
 
+class _AttentionSoftmax(torch.autograd.Function):
+    """a[e,h] = softmax over the in-edges of v_e of  w[e,h] * leaky_relu(el[u_e,h] + er[v_e,h])  -- GAT's attention
+    (stag/zoo/gat.py:113-122) without the [E,H] logits and their autograd graph (stag_attention_softmax).  Backward: one
+    pass over the CSC rows gives d w, d er and the per-edge d(el + er); d el is their sum per SOURCE node, taken by the
+    aggregation kernel on the CSR (edge values as external weights of a ones operand).  No atomics: deterministic."""
+
+    @staticmethod
+    def forward(ctx, el, er, w, g, slope):
+        _require_cuda(el, "el")
+        lib = _lib.load()
+        dev = el.device
+        st = g._s
+        E, H = st.num_edges, el.shape[-1]
+        elc, erc = el.detach().to(torch.float32).contiguous(), er.detach().to(torch.float32).contiguous()
+        wc = None if w is None else w.detach().to(torch.float32).contiguous()
+        a = torch.empty((E, H), dtype=torch.float32, device=dev)
+        with _on_device(dev):
+            csc, _ = st.csx(True)
+            _lib.check(lib.stag_attention_softmax(ctypes.byref(csc), elc.data_ptr(), erc.data_ptr(), _ptr(wc), float(slope), H,
+                                                  a.data_ptr(), _stream(dev)))
+        ctx.g, ctx.slope = g, float(slope)
+        ctx.save_for_backward(elc, erc, wc, a)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        elc, erc, wc, a = ctx.saved_tensors
+        lib = _lib.load()
+        dev = a.device
+        st = ctx.g._s
+        E, H = a.shape
+        d_er = torch.zeros_like(erc)
+        d_el = torch.zeros_like(elc)
+        dw = None
+        if E:
+            da = da.to(torch.float32).contiguous()
+            dw = torch.empty_like(a) if (wc is not None and ctx.needs_input_grad[2]) else None
+            dpre = torch.empty_like(a)
+            with _on_device(dev):
+                csc, _ = st.csx(True)
+                _lib.check(lib.stag_attention_softmax_bwd(
+                    ctypes.byref(csc), elc.data_ptr(), erc.data_ptr(), _ptr(wc), ctx.slope, H, a.data_ptr(), da.data_ptr(),
+                    _ptr(dw), dpre.data_ptr(), d_er.data_ptr(), _stream(dev)))
+                if ctx.needs_input_grad[0]:
+                    # d el[u,h] = sum over the out-edges of u of dpre[e,h]: the aggregation kernel on the CSR, a ones operand
+                    # gathered per destination, the edge values as external per-channel weights
+                    csr, _ = st.csx(False)
+                    ws = _workspace(st, lib, csr, False, H, 1)
+                    ones = torch.ones((st.num_nodes, H), dtype=torch.float32, device=dev)
+                    nz = _fill_noise(None, _lib.NOISE_EXTERNAL, H, None, None, dpre, False, False, 0, 0, 0, _lib.PARAM_SCALAR)
+                    _lib.check(lib.stag_spmm_fwd(
+                        ctypes.byref(csr), ones.data_ptr(), H, 0, H, 1, ctypes.byref(nz), 0, 0, d_el.data_ptr(), H,
+                        st.num_src * H, 0, ws.data_ptr(), ws.numel(), _stream(dev)))
+        elif wc is not None and ctx.needs_input_grad[2]:
+            dw = torch.zeros_like(a)
+        return d_el, d_er, dw, None, None
+
+
+def attention_softmax(graph, el, er, edge_weight=None, negative_slope=0.2):
+    """GAT attention ``[E,H]`` from the per-node scores ``el [N_src,H]``, ``er [N,H]`` and optional edge noise ``[E,H]``
+    (see :class:`_AttentionSoftmax`)."""
+    g = as_graph(graph)
+    E = g.number_of_edges()
+    if el.dim() != 2 or er.dim() != 2 or el.shape[1] != er.shape[1]:
+        raise ValueError("attention_softmax: el [N_src,H] and er [N,H] expected, got %s and %s" % (tuple(el.shape), tuple(er.shape)))
+    w = edge_weight
+    if w is not None:
+        w = w.unsqueeze(-1) if w.dim() == 1 else w.flatten(1)
+        if w.shape[0] != E or w.shape[1] not in (1, el.shape[1]):
+            raise ValueError("attention_softmax: edge_weight must be [E,H] or [E,1], got %s" % (tuple(edge_weight.shape),))
+        w = w.expand(E, el.shape[1])
+    return _AttentionSoftmax.apply(el, er, w, g, negative_slope)
+
+
 def edge_softmax(graph, logits):
     """Softmax of ``logits [E,H]`` (or ``[E]``) over the in-edges of each destination node."""
     g = as_graph(graph)

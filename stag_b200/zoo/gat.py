@@ -64,11 +64,9 @@ class GAT(nn.Module):
         ft = self.fc(h).view(N, H, F)
         el = (ft * self.attn_l).sum(dim=-1)
         er = (ft * self.attn_r).sum(dim=-1)
-        e = self.leaky_relu(el[src] + er[dst])                     # [E,H]
-        if edge_weight is not None:
-            e = edge_weight * e
-        # segmented softmax over the in-edges of each node: one fused pass (stag_edge_softmax)
-        a = self.attn_drop(ops.edge_softmax(g, e))                 # [E,H]
+        # attention: softmax over the in-edges of  edge_weight * leaky_relu(el[u] + er[v])  in one fused pass per direction
+        # (stag_attention_softmax: the [E,H] logits and their autograd graph never exist)
+        a = self.attn_drop(ops.attention_softmax(g, el, er, edge_weight, self.leaky_relu.negative_slope))   # [E,H]
         if a.shape[0] * H * F * 4 <= (4 << 20):
             # small graphs are launch-bound: ONE fused launch over the H*F channels, the attention of head k expanded to the
             # weight of channels k*F .. (k+1)*F - 1 (external per-channel weights [E, H*F], at most 4 MB; autograd sums the

@@ -352,3 +352,53 @@ def test_gat_layer_takes_the_per_head_route_on_larger_graphs(monkeypatch):
     assert rel(res[0][0], res[1][0]) < 1e-5
     for ga, gb in zip(res[0][1], res[1][1]):
         assert rel(ga, gb) < 1e-4
+
+
+@pytest.mark.parametrize("N,E,H,with_w", [(500, 4000, 4, True), (300, 2500, 3, True), (2000, 30000, 8, False),
+                                          (400, 3000, 1, True), (50, 0, 4, True), (900, 9000, 5, True)])
+def test_attention_softmax_against_the_torch_formulation(N, E, H, with_w):
+    """stag_attention_softmax (logits w * leaky_relu(el[u] + er[v]) computed inside the segmented softmax) against the
+    reference's chain in float64 (stag/zoo/gat.py:113-122: u_add_v, leaky_relu, noise product, edge_softmax): the
+    attention and its gradients w.r.t. el, er and the edge noise; nodes without in-edges, a hub, any number of heads."""
+    import stag_b200 as stag
+    rng = np.random.default_rng(N + E + H)
+    src, dst = rng.integers(0, N, E), rng.integers(0, N - 7, E)       # the last 7 nodes have no in-edges
+    if E > 5000:
+        dst[:2000] = 3
+    T = torch.from_numpy
+    g = stag.Graph(T(src), T(dst), N).to("cuda")
+    el0 = T(rng.standard_normal((N, H)).astype(np.float32)).cuda()
+    er0 = T(rng.standard_normal((N, H)).astype(np.float32)).cuda()
+    w0 = T((1 + 0.4 * rng.standard_normal((E, H))).astype(np.float32)).cuda() if with_w else None
+    da = T(rng.standard_normal((E, H)).astype(np.float32)).cuda()
+    el, er = el0.clone().requires_grad_(True), er0.clone().requires_grad_(True)
+    w = None if w0 is None else w0.clone().requires_grad_(True)
+    a = stag.ops.attention_softmax(g, el, er, w, 0.2)
+    assert a.shape == (E, H)
+    a.backward(da)
+    # float64 scatter formulation
+    eld, erd = el0.double().requires_grad_(True), er0.double().requires_grad_(True)
+    wd = None if w0 is None else w0.double().requires_grad_(True)
+    s_, d_ = T(src).cuda(), T(dst).cuda()
+    lg = torch.nn.functional.leaky_relu(eld[s_] + erd[d_], 0.2)
+    if wd is not None:
+        lg = lg * wd
+    if E:
+        m = torch.full((N, H), -float("inf"), dtype=torch.float64, device="cuda").scatter_reduce(
+            0, d_[:, None].expand(E, H), lg, "amax", include_self=True)
+        ex = torch.exp(lg - m[d_])
+        ref = ex / torch.zeros(N, H, dtype=torch.float64, device="cuda").index_add(0, d_, ex)[d_]
+        ref.backward(da.double())
+        rel = lambda u, v: float((u.double() - v).abs().max() / v.abs().max().clamp(min=1e-30))  # noqa: E731
+        assert rel(a.detach(), ref.detach()) < 1e-5
+        assert rel(el.grad, eld.grad) < 2e-5 and rel(er.grad, erd.grad) < 2e-5
+        if w is not None:
+            assert rel(w.grad, wd.grad) < 2e-5
+        sums = torch.zeros(N, H, device="cuda").index_add(0, d_, a.detach())
+        assert float((sums[: N - 7][torch.bincount(d_, minlength=N)[: N - 7] > 0] - 1).abs().max()) < 1e-5
+        # run-to-run bitwise (no atomics)
+        el2, er2 = el0.clone().requires_grad_(True), er0.clone().requires_grad_(True)
+        stag.ops.attention_softmax(g, el2, er2, w0, 0.2).backward(da)
+        assert torch.equal(el2.grad, el.grad) and torch.equal(er2.grad, er.grad)
+    else:
+        assert float(el.grad.abs().sum()) == 0.0 and float(er.grad.abs().sum()) == 0.0
