@@ -1,9 +1,10 @@
 """``GAT`` -- constructor and forward of the reference's ``stag.zoo.GAT`` (stag/zoo/gat.py:7-149).
-The noise ``[E,H]`` multiplies the pre-softmax logits (:117-119).  The segmented softmax over the in-edges of each
-node runs on ``stag_edge_softmax`` (forward and backward in one fused pass each, csrc/edge_softmax.cu) and the final
-weighted aggregation ``update_all(u_mul_e('ft','a'), sum)`` (:125-126) on ``stag_spmm_fwd`` with the attention as
+The noise ``[E,H]`` multiplies the pre-softmax logits (:117-119).  Attention: the logits
+``edge_weight * leaky_relu(el[u] + er[v])`` are computed INSIDE the segmented softmax over the in-edges of each node
+(``stag_attention_softmax``, forward and a deterministic backward, csrc/edge_softmax.cu: no ``[E,H]`` logits, no atomics).
+The weighted aggregation ``update_all(u_mul_e('ft','a'), sum)`` (:125-126) runs on ``stag_spmm_fwd`` with the attention as
 external weights: all heads in one launch with expanded ``[E, H*F]`` weights on small (launch-bound) graphs (<= 4 MB),
-else ``ops.heads_aggregate`` -- one launch per head, every head reading / writing its F columns in place.  The logits and the noise product are elementwise torch ops on ``[E,H]``.
+else ``ops.heads_aggregate`` -- one launch per head, every head reading / writing its F columns in place.
 ``accepts_noise_spec`` is False: the noise multiplies the LOGITS, not the messages, so ``StagLayer`` hands this
 layer a tensor emitted from the library's Philox stream (``stag_noise_emit``, K = num_heads).
 """
