@@ -256,3 +256,22 @@ def test_generator_selection_rules_of_a_noise_spec():
     assert NoiseSpec("uniform", one, 2 * one, 128, 10).lib_kind == _lib.NOISE_UNIFORM
     with pytest.raises(ValueError):
         NoiseSpec("normal", one, one, 128, 10, generator="ziggurat")
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU (it times the C/OpenMP restatement of the reference algorithm on the host
+    cores): one JSON line with the arm's metric / unit / config and the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "GEdge-samples/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] == 1 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"] and line["gpu_launches"] == 0
