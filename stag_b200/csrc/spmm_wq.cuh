@@ -19,6 +19,8 @@
 //   NW = 8: warps w and w + 4 share quadrant w % 4 and take one channel half each (16 channels per thread, half the
 //           registers, twice the warps to hide the TMEM / shared-memory / barrier latencies behind).
 //   DB: two TMEM accumulators (256 columns), the MMAs of round r + 1 run under the consumption of round r.
+//   CTA items (32 stream items each) are handed out by a work queue; template switches GMODE / LATE_REC (where the
+//   gathers are re-issued, when the records of a round are read) are documented at the kernel.
 #pragma once
 
 namespace stag {
